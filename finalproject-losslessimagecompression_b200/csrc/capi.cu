@@ -1,0 +1,455 @@
+// capi.cu -- the C ABI declared in include/flic_b200.h.
+//
+// Thin: argument checks, workspace carving, launches.  The host entry points add the
+// host<->device copies (chunked and double-buffered over two CUDA streams so that the PCIe
+// transfer of one chunk overlaps the kernels of the previous one) and one synchronisation.
+#include "../../include/flic_b200.h"
+#include "flic_core.cuh"
+#include "flic_kernels.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+#define FLIC_CUDA(call)                                         \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+    } while (0)
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Workspace layout for one encode call: [scratch u32 x n_symbols][counts i64 x n_streams][scan tmp]
+struct EncodeWorkspace {
+    uint32_t* scratch;
+    int64_t* counts;
+    int64_t* scan_tmp;
+    int64_t bytes;
+};
+
+EncodeWorkspace carve(void* base, int64_t n_symbols, int64_t n_streams) {
+    EncodeWorkspace w;
+    char* p = (char*)base;
+    int64_t off = 0;
+    w.scratch = (uint32_t*)(p + off);
+    off = align_up(off + (int64_t)sizeof(uint32_t) * (n_symbols > 0 ? n_symbols : 1), 256);
+    w.counts = (int64_t*)(p + off);
+    off = align_up(off + (int64_t)sizeof(int64_t) * (n_streams > 0 ? n_streams : 1), 256);
+    w.scan_tmp = (int64_t*)(p + off);
+    off = align_up(off + (int64_t)sizeof(int64_t) * flic::scan_tmp_elems(n_streams > 0 ? n_streams : 1), 256);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flic_abi_version(void) { return FLIC_ABI_VERSION; }
+const char* flic_last_error(void) { return g_err; }
+int64_t flic_kernel_launches(void) { return g_launches.load(); }
+
+int flic_cdf_tables(const float* x, const float* mean, const float* scale, int64_t n_symbols,
+                    uint32_t* start, uint32_t* freq, int32_t* status_word,
+                    flic_cuda_stream_t stream) {
+    if (n_symbols < 0) return fail(FLIC_E_ARG, "n_symbols < 0");
+    if (n_symbols == 0) return 0;
+    if (!x || !mean || !scale || !start || !freq || !status_word) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_cdf_tables(x, mean, scale, n_symbols, start, freq, status_word, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int64_t flic_encode_workspace_bytes(int64_t n_symbols, int64_t n_streams) {
+    return carve(nullptr, n_symbols, n_streams).bytes;
+}
+
+int flic_rans_encode(const float* x, const float* mean, const float* scale,
+                     const int64_t* stream_offsets, int64_t n_streams, int64_t n_symbols,
+                     const uint64_t* init_states, void* workspace, int64_t workspace_bytes,
+                     uint32_t* packed, int64_t packed_capacity, int64_t* word_offsets,
+                     uint64_t* final_states, int32_t* status, flic_cuda_stream_t stream) {
+    if (n_streams < 0 || n_symbols < 0) return fail(FLIC_E_ARG, "negative size");
+    if (!word_offsets) return fail(FLIC_E_ARG, "null word_offsets");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_streams == 0) {
+        FLIC_CUDA(cudaMemsetAsync(word_offsets, 0, sizeof(int64_t), st));
+        return 0;
+    }
+    if (!stream_offsets || !workspace || !final_states || !status) return fail(FLIC_E_ARG, "null pointer");
+    if (n_symbols > 0 && (!x || !mean || !scale || !packed)) return fail(FLIC_E_ARG, "null pointer");
+    const EncodeWorkspace w = carve(workspace, n_symbols, n_streams);
+    if (workspace_bytes < w.bytes)
+        return fail(FLIC_E_CAPACITY, "workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w.bytes);
+    FLIC_CUDA(flic::launch_rans_encode(x, mean, scale, stream_offsets, n_streams, init_states, w.scratch,
+                                       w.counts, final_states, status, st));
+    FLIC_CUDA(flic::launch_scan_counts(w.counts, n_streams, word_offsets, w.scan_tmp, st));
+    FLIC_CUDA(flic::launch_pack_words(w.scratch, stream_offsets, word_offsets, n_streams, packed,
+                                      packed_capacity, status, st));
+    g_launches += 5;
+    return 0;
+}
+
+int flic_rans_decode(const uint32_t* packed, const int64_t* word_offsets,
+                     const uint64_t* final_states, const float* mean, const float* scale,
+                     const int64_t* stream_offsets, int64_t n_streams, float* x_out,
+                     uint64_t* end_states, int32_t* status, int check_end,
+                     flic_cuda_stream_t stream) {
+    if (n_streams < 0) return fail(FLIC_E_ARG, "n_streams < 0");
+    if (n_streams == 0) return 0;
+    if (!word_offsets || !final_states || !stream_offsets || !end_states || !status)
+        return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_rans_decode(packed, word_offsets, final_states, mean, scale, stream_offsets,
+                                       n_streams, x_out, end_states, status, check_end, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_couple_add_round(float* x, const float* t, int64_t batch, int64_t channels, int64_t a_ch,
+                          int64_t hw, int direction, int nbits, flic_cuda_stream_t stream) {
+    if (batch < 0 || channels < 0 || a_ch < 0 || a_ch > channels || hw < 0) return fail(FLIC_E_ARG, "bad shape");
+    if (direction != 1 && direction != -1) return fail(FLIC_E_ARG, "direction must be +1 or -1");
+    if (nbits < 0 || nbits > 23) return fail(FLIC_E_ARG, "nbits out of range");
+    if (batch * (channels - a_ch) * hw == 0) return 0;
+    if (!x || !t) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_couple_add_round(x, t, batch, channels, a_ch, hw, (float)direction, nbits,
+                                            (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_u8_to_grid(const uint8_t* src, float* dst, int64_t n, flic_cuda_stream_t stream) {
+    if (n < 0) return fail(FLIC_E_ARG, "n < 0");
+    if (n == 0) return 0;
+    if (!src || !dst) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_u8_to_grid(src, dst, n, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_grid_to_u8(const float* src, uint8_t* dst, int64_t n, int32_t* status_word,
+                    flic_cuda_stream_t stream) {
+    if (n < 0) return fail(FLIC_E_ARG, "n < 0");
+    if (n == 0) return 0;
+    if (!src || !dst || !status_word) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_grid_to_u8(src, dst, n, status_word, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_permute_channels(const float* src, float* dst, const int32_t* perm, int64_t batch,
+                          int64_t channels, int64_t hw, flic_cuda_stream_t stream) {
+    if (batch < 0 || channels < 0 || hw < 0) return fail(FLIC_E_ARG, "bad shape");
+    if (batch * channels * hw == 0) return 0;
+    if (!src || !dst || !perm || src == dst) return fail(FLIC_E_ARG, "null or aliased pointer");
+    FLIC_CUDA(flic::launch_permute_channels(src, dst, perm, batch, channels, hw, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_squeeze(const float* src, float* dst, int64_t batch, int64_t C, int64_t H, int64_t W,
+                 int scale, int direction, flic_cuda_stream_t stream) {
+    if (batch < 0 || C < 0 || H < 0 || W < 0 || scale < 1) return fail(FLIC_E_ARG, "bad shape");
+    if (H % scale || W % scale) return fail(FLIC_E_ARG, "H, W must be multiples of scale");
+    if (direction != 1 && direction != -1) return fail(FLIC_E_ARG, "direction must be +1 or -1");
+    if (batch * C * H * W == 0) return 0;
+    if (!src || !dst || src == dst) return fail(FLIC_E_ARG, "null or aliased pointer");
+    FLIC_CUDA(flic::launch_squeeze(src, dst, batch, C, H, W, scale, direction, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Host entry points
+ * ------------------------------------------------------------------------------------------ */
+
+struct flic_codec {
+    int device;
+    int64_t max_symbols, max_streams;
+    // Two pipeline slots; each can hold a chunk of up to slot_symbols symbols / slot_streams streams.
+    static constexpr int kSlots = 2;
+    int64_t slot_symbols, slot_streams;
+    cudaStream_t streams[kSlots];
+    cudaEvent_t done[kSlots];
+    struct Slot {
+        float *x, *mean, *scale;
+        int64_t* offsets;       // chunk-local stream offsets
+        uint32_t* packed;
+        int64_t* word_offsets;
+        uint64_t* states;
+        uint64_t* end_states;
+        int32_t* status;
+        void* workspace;
+        int64_t workspace_bytes;
+        int64_t* h_offsets;     // pinned staging: chunk-local offsets / word offsets
+        int64_t* h_word_offsets;
+    } slot[kSlots];
+};
+
+static void codec_free(flic_codec* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < flic_codec::kSlots; ++i) {
+        flic_codec::Slot& s = c->slot[i];
+        cudaFree(s.x); cudaFree(s.mean); cudaFree(s.scale); cudaFree(s.offsets); cudaFree(s.packed);
+        cudaFree(s.word_offsets); cudaFree(s.states); cudaFree(s.end_states); cudaFree(s.status);
+        cudaFree(s.workspace);
+        cudaFreeHost(s.h_offsets); cudaFreeHost(s.h_word_offsets);
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        if (c->done[i]) cudaEventDestroy(c->done[i]);
+    }
+    delete c;
+}
+
+int flic_codec_create(int device, int64_t max_symbols, int64_t max_streams, flic_codec** out) {
+    if (!out || max_symbols < 1 || max_streams < 1) return fail(FLIC_E_ARG, "bad codec size");
+    flic_codec* c = new (std::nothrow) flic_codec();
+    if (!c) return fail(FLIC_E_NOMEM, "out of host memory");
+    memset((void*)c, 0, sizeof *c);
+    c->device = device;
+    c->max_symbols = max_symbols;
+    c->max_streams = max_streams;
+    // A slot holds the whole call when it is small, otherwise ~64 Mi symbols (768 MB of inputs)
+    // so that two chunks in flight overlap copy and compute without a huge footprint.  A single
+    // stream longer than a slot is still accepted by growing the slot to max_symbols.
+    c->slot_symbols = max_symbols;
+    c->slot_streams = max_streams;
+    cudaError_t e = cudaSetDevice(device);
+    for (int i = 0; e == cudaSuccess && i < flic_codec::kSlots; ++i) {
+        flic_codec::Slot& s = c->slot[i];
+        const int64_t ns = c->slot_symbols, nt = c->slot_streams;
+        s.workspace_bytes = flic_encode_workspace_bytes(ns, nt);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&s.x, sizeof(float) * ns);
+        if (e == cudaSuccess) e = cudaMalloc(&s.mean, sizeof(float) * ns);
+        if (e == cudaSuccess) e = cudaMalloc(&s.scale, sizeof(float) * ns);
+        if (e == cudaSuccess) e = cudaMalloc(&s.offsets, sizeof(int64_t) * (nt + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&s.packed, sizeof(uint32_t) * ns);
+        if (e == cudaSuccess) e = cudaMalloc(&s.word_offsets, sizeof(int64_t) * (nt + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&s.states, sizeof(uint64_t) * nt);
+        if (e == cudaSuccess) e = cudaMalloc(&s.end_states, sizeof(uint64_t) * nt);
+        if (e == cudaSuccess) e = cudaMalloc(&s.status, sizeof(int32_t) * nt);
+        if (e == cudaSuccess) e = cudaMalloc(&s.workspace, (size_t)s.workspace_bytes);
+        if (e == cudaSuccess) e = cudaMallocHost(&s.h_offsets, sizeof(int64_t) * (nt + 1));
+        if (e == cudaSuccess) e = cudaMallocHost(&s.h_word_offsets, sizeof(int64_t) * (nt + 1));
+    }
+    if (e != cudaSuccess) {
+        codec_free(c);
+        return cuda_fail(e, "flic_codec_create");
+    }
+    *out = c;
+    return 0;
+}
+
+void flic_codec_destroy(flic_codec* codec) { codec_free(codec); }
+
+int flic_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(FLIC_E_ARG, "bad host alloc");
+    FLIC_CUDA(cudaMallocHost(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return 0;
+}
+
+void flic_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+static int check_offsets(const int64_t* off, int64_t n_streams) {
+    if (off[0] != 0) return fail(FLIC_E_ARG, "stream_offsets[0] != 0");
+    for (int64_t s = 0; s < n_streams; ++s)
+        if (off[s + 1] < off[s]) return fail(FLIC_E_ARG, "stream_offsets not monotone at %lld", (long long)s);
+    return 0;
+}
+
+int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const float* scale,
+                      const int64_t* stream_offsets, int64_t n_streams, uint32_t* words_out,
+                      int64_t words_capacity, int64_t* word_offsets_out, uint64_t* states_out,
+                      int32_t* status_out, int64_t* n_words_out) {
+    if (!c || n_streams < 0 || !stream_offsets || !word_offsets_out) return fail(FLIC_E_ARG, "bad argument");
+    if (int rc = check_offsets(stream_offsets, n_streams)) return rc;
+    const int64_t n_symbols = stream_offsets[n_streams];
+    if (n_symbols > c->max_symbols || n_streams > c->max_streams)
+        return fail(FLIC_E_CAPACITY, "codec sized for %lld symbols / %lld streams", (long long)c->max_symbols,
+                    (long long)c->max_streams);
+    word_offsets_out[0] = 0;
+    if (n_words_out) *n_words_out = 0;
+    if (n_streams == 0) return 0;
+    if (!states_out || !status_out || (n_symbols > 0 && (!x || !mean || !scale || !words_out)))
+        return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(cudaSetDevice(c->device));
+    flic_codec::Slot& s = c->slot[0];
+    cudaStream_t st = c->streams[0];
+    FLIC_CUDA(cudaMemcpyAsync(s.x, x, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.mean, mean, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.scale, scale, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.offsets, stream_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyHostToDevice, st));
+    if (int rc = flic_rans_encode(s.x, s.mean, s.scale, s.offsets, n_streams, n_symbols, nullptr, s.workspace,
+                                  s.workspace_bytes, s.packed, n_symbols > 0 ? n_symbols : 1, s.word_offsets,
+                                  s.states, s.status, st))
+        return rc;
+    FLIC_CUDA(cudaMemcpyAsync(word_offsets_out, s.word_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaMemcpyAsync(states_out, s.states, sizeof(uint64_t) * n_streams, cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaMemcpyAsync(status_out, s.status, sizeof(int32_t) * n_streams, cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaStreamSynchronize(st));
+    const int64_t total = word_offsets_out[n_streams];
+    if (n_words_out) *n_words_out = total;
+    if (total > words_capacity)
+        return fail(FLIC_E_CAPACITY, "words_out holds %lld words, %lld needed", (long long)words_capacity, (long long)total);
+    if (total > 0) {
+        FLIC_CUDA(cudaMemcpyAsync(words_out, s.packed, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
+        FLIC_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_offsets,
+                      const uint64_t* states, const float* mean, const float* scale,
+                      const int64_t* stream_offsets, int64_t n_streams, float* x_out,
+                      uint64_t* end_states_out, int32_t* status_out) {
+    if (!c || n_streams < 0 || !stream_offsets || !word_offsets) return fail(FLIC_E_ARG, "bad argument");
+    if (n_streams == 0) return 0;
+    if (int rc = check_offsets(stream_offsets, n_streams)) return rc;
+    if (int rc = check_offsets(word_offsets, n_streams)) return rc;
+    const int64_t n_symbols = stream_offsets[n_streams];
+    const int64_t n_words = word_offsets[n_streams];
+    if (n_symbols > c->max_symbols || n_streams > c->max_streams || n_words > c->max_symbols)
+        return fail(FLIC_E_CAPACITY, "codec sized for %lld symbols / %lld streams", (long long)c->max_symbols,
+                    (long long)c->max_streams);
+    if (!states || !status_out || (n_symbols > 0 && (!mean || !scale || !x_out)) || (n_words > 0 && !words))
+        return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(cudaSetDevice(c->device));
+    flic_codec::Slot& s = c->slot[0];
+    cudaStream_t st = c->streams[0];
+    if (n_words > 0)
+        FLIC_CUDA(cudaMemcpyAsync(s.packed, words, sizeof(uint32_t) * n_words, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.word_offsets, word_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.states, states, sizeof(uint64_t) * n_streams, cudaMemcpyHostToDevice, st));
+    if (n_symbols > 0) {
+        FLIC_CUDA(cudaMemcpyAsync(s.mean, mean, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
+        FLIC_CUDA(cudaMemcpyAsync(s.scale, scale, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
+    }
+    FLIC_CUDA(cudaMemcpyAsync(s.offsets, stream_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyHostToDevice, st));
+    if (int rc = flic_rans_decode(s.packed, s.word_offsets, s.states, s.mean, s.scale, s.offsets, n_streams, s.x,
+                                  s.end_states, s.status, 1, st))
+        return rc;
+    if (n_symbols > 0)
+        FLIC_CUDA(cudaMemcpyAsync(x_out, s.x, sizeof(float) * n_symbols, cudaMemcpyDeviceToHost, st));
+    if (end_states_out)
+        FLIC_CUDA(cudaMemcpyAsync(end_states_out, s.end_states, sizeof(uint64_t) * n_streams, cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaMemcpyAsync(status_out, s.status, sizeof(int32_t) * n_streams, cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int flic_rans_encode_single(flic_codec* c, uint64_t state, int64_t n, const float* x,
+                            const float* mean, const float* scale, uint32_t* buffer_out,
+                            int64_t* n_words_out, uint64_t* state_out, int32_t* status_out) {
+    if (!c || n < 0 || !n_words_out || !state_out) return fail(FLIC_E_ARG, "bad argument");
+    if (n > c->max_symbols) return fail(FLIC_E_CAPACITY, "codec sized for %lld symbols", (long long)c->max_symbols);
+    *n_words_out = 0;
+    *state_out = state;
+    if (status_out) *status_out = 0;
+    if (n == 0) return 0;
+    if (!x || !mean || !scale || !buffer_out) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(cudaSetDevice(c->device));
+    flic_codec::Slot& s = c->slot[0];
+    cudaStream_t st = c->streams[0];
+    const int64_t offs[2] = {0, n};
+    int64_t woffs[2] = {0, 0};
+    int32_t status = 0;
+    FLIC_CUDA(cudaMemcpyAsync(s.x, x, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.mean, mean, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.scale, scale, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.offsets, offs, sizeof offs, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaMemcpyAsync(s.end_states, &state, sizeof state, cudaMemcpyHostToDevice, st));
+    FLIC_CUDA(cudaStreamSynchronize(st));  // offs / state live on this stack frame
+    if (int rc = flic_rans_encode(s.x, s.mean, s.scale, s.offsets, 1, n, s.end_states, s.workspace,
+                                  s.workspace_bytes, s.packed, n, s.word_offsets, s.states, s.status, st))
+        return rc;
+    FLIC_CUDA(cudaMemcpyAsync(woffs, s.word_offsets, sizeof woffs, cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaMemcpyAsync(state_out, s.states, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaMemcpyAsync(&status, s.status, sizeof status, cudaMemcpyDeviceToHost, st));
+    FLIC_CUDA(cudaStreamSynchronize(st));
+    *n_words_out = woffs[1];
+    if (status_out) *status_out = status;
+    if (woffs[1] > 0) {
+        FLIC_CUDA(cudaMemcpyAsync(buffer_out, s.packed, sizeof(uint32_t) * woffs[1], cudaMemcpyDeviceToHost, st));
+        FLIC_CUDA(cudaStreamSynchronize(st));
+    }
+    if (status) return fail(FLIC_E_STATUS, "stream status 0x%x", status);
+    return 0;
+}
+
+int flic_rans_decode_single(flic_codec* c, uint64_t state, const uint32_t* buffer_reversed,
+                            int64_t n_buffer, int64_t n, const float* mean_reversed,
+                            const float* scale_reversed, float* message_out, uint64_t* state_out,
+                            int32_t* status_out) {
+    if (!c || n < 0 || n_buffer < 0 || !state_out) return fail(FLIC_E_ARG, "bad argument");
+    if (n > c->max_symbols || n_buffer > c->max_symbols)
+        return fail(FLIC_E_CAPACITY, "codec sized for %lld symbols", (long long)c->max_symbols);
+    *state_out = state;
+    if (status_out) *status_out = 0;
+    if (n == 0) return 0;
+    if (!mean_reversed || !scale_reversed || !message_out || (n_buffer > 0 && !buffer_reversed))
+        return fail(FLIC_E_ARG, "null pointer");
+    // Undo the caller's reversal (trainer.py:317) on the host; the kernel walks streams backwards.
+    float* fm = (float*)malloc(sizeof(float) * (size_t)n * 2);
+    uint32_t* fb = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n_buffer > 0 ? n_buffer : 1));
+    if (!fm || !fb) { free(fm); free(fb); return fail(FLIC_E_NOMEM, "out of host memory"); }
+    float* fs = fm + n;
+    for (int64_t i = 0; i < n; ++i) { fm[i] = mean_reversed[n - 1 - i]; fs[i] = scale_reversed[n - 1 - i]; }
+    for (int64_t i = 0; i < n_buffer; ++i) fb[i] = buffer_reversed[n_buffer - 1 - i];
+    const int64_t offs[2] = {0, n};
+    const int64_t woffs[2] = {0, n_buffer};
+    int32_t status = 0;
+    int rc = 0;
+    cudaError_t e = cudaSetDevice(c->device);
+    flic_codec::Slot& s = c->slot[0];
+    cudaStream_t st = c->streams[0];
+    if (e == cudaSuccess && n_buffer > 0) e = cudaMemcpyAsync(s.packed, fb, sizeof(uint32_t) * n_buffer, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.mean, fm, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.scale, fs, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.offsets, offs, sizeof offs, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.word_offsets, woffs, sizeof woffs, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.states, &state, sizeof state, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+        rc = flic_rans_decode(s.packed, s.word_offsets, s.states, s.mean, s.scale, s.offsets, 1, s.x, s.end_states,
+                              s.status, 0, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(fm, s.x, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(state_out, s.end_states, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(&status, s.status, sizeof status, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && rc == 0)
+        for (int64_t i = 0; i < n; ++i) message_out[i] = fm[n - 1 - i];
+    free(fm);
+    free(fb);
+    if (e != cudaSuccess) return cuda_fail(e, "flic_rans_decode_single");
+    if (rc) return rc;
+    if (status_out) *status_out = status;
+    if (status) return fail(FLIC_E_STATUS, "stream status 0x%x", status);
+    return 0;
+}
+
+}  // extern "C"

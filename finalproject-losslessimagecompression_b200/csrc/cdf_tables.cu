@@ -1,0 +1,43 @@
+// K1 -- fused CDF evaluation + 24-bit frequency quantisation.
+//
+// Replaces encode pass 1 of the reference (rans/rans.pyx:49-56, generated C rans/rans.cpp:1668-1755)
+// plus the two CDF() calls per symbol (rans.pyx:31-35).  One thread per symbol, grid-stride,
+// fully coalesced 4-byte loads of x / mean / scale and 4-byte stores of start / freq
+// (algorithmic traffic 12 B in + 8 B out per symbol).  The arithmetic is FP64-heavy (two
+// correctly-rounded reciprocals, two glibc-expf evaluations), so this kernel is bound by the
+// FP64 / conversion pipes rather than by HBM; see DESIGN.md for the roofline.
+#include "flic_device.cuh"
+#include "flic_kernels.cuh"
+
+namespace flic {
+
+__global__ void __launch_bounds__(256)
+cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                  const float* __restrict__ scale, int64_t n, uint32_t* __restrict__ start,
+                  uint32_t* __restrict__ freq, int32_t* __restrict__ status_word) {
+    __shared__ uint64_t s_tab[32];
+    stage_exp_table(s_tab);
+    int32_t flags = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const SymbolTable t = make_table(__ldg(x + i), __ldg(mean + i), __ldg(scale + i), s_tab, flags);
+        start[i] = t.start;
+        freq[i] = t.freq;
+    }
+    if (flags) atomicOr(status_word, flags);
+}
+
+cudaError_t launch_cdf_tables(const float* x, const float* mean, const float* scale, int64_t n,
+                              uint32_t* start, uint32_t* freq, int32_t* status_word,
+                              cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int sms = sm_count();
+    const int threads = 256;
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    cdf_tables_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, mean, scale, n, start, freq, status_word);
+    return cudaGetLastError();
+}
+
+}  // namespace flic

@@ -1,0 +1,413 @@
+// flic_core.cuh -- bit-exact arithmetic of the reference coder, written once for the device.
+//
+// Everything the kernels need to reproduce rans/rans.pyx on sm_100a lives here as
+// __host__ __device__ inline functions:
+//   * expf_glibc()    glibc >= 2.27 expf algorithm (sysdeps/ieee754/flt-32/e_expf.c), which is
+//                     what the reference links (expf@GLIBC_2.27, rans/rans.cpp:1301)
+//   * lower_of()      window origin                       rans/rans.pyx:51,92  (rans.cpp:1683,2145)
+//   * SymbolModel     per-symbol constants shared by every CDF evaluation of that symbol
+//   * cdf_at()        CDF(s/256) = part1 + part2          rans/rans.pyx:31-35  (rans.cpp:1418-1449)
+//   * rans_push()     encoder renorm + state update       rans/rans.pyx:61-66  (rans.cpp:1765-1845)
+//   * rans_pop_*()    decoder renorm / state update       rans/rans.pyx:87-90,108
+//   * search_symbol() smallest s in the window with CDF(s) > mod   rans/rans.pyx:92-104
+// The float/double promotion order follows the reference's generated C++.
+// Every IEEE operation whose rounding matters goes through dadd/dsub/dmul/dfma below so that
+// neither nvcc nor the host compiler can contract or reassociate it.
+//
+// The same header compiles with plain g++ (tests/host_harness.cpp) so that the search / rANS
+// logic is checked against the oracle on the CPU before any GPU time is spent.  That harness is
+// test infrastructure; the product never runs these functions on the host.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define FLIC_HD __host__ __device__ __forceinline__
+#else
+#define FLIC_HD static inline
+#endif
+
+namespace flic {
+
+// ---- status bits (per stream), a superset of the reference's exceptions ----------------------
+enum : int32_t {
+    ST_OK = 0,
+    ST_ZERO_SCALE = 1,     // reference: ZeroDivisionError "float division" (rans.cpp:1435-1437)
+    ST_OUT_OF_WINDOW = 2,  // reference: silent corruption; flagged here
+    ST_UNDERRUN = 4,       // reference: unchecked buffer[pos] (rans.cpp:2109); flagged here
+    ST_NONFINITE = 8,      // NaN/inf scale, or |mean| > 16384 (window arithmetic no longer exact)
+    ST_BAD_END_STATE = 16, // decoder did not return to 1<<32 (rans/test.py:26 prints it)
+    ST_NO_SYMBOL = 32,     // decoder: mod >= CDF(upper); reference would emit lower+2048
+};
+
+constexpr uint64_t kRansL = 0x100000000ull;  // rans.pyx:13
+constexpr uint32_t kProbMask = 0xffffffu;    // rans.pyx:90
+constexpr int kWindow = 2048;                // rans.pyx:22
+constexpr double kPart1Scale = 16775168.0;   // M - 2048, rans.pyx:34
+
+// ---- IEEE primitives that must not be contracted ----------------------------------------------
+FLIC_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+FLIC_HD double dsub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+FLIC_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+FLIC_HD double dfma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+// correctly rounded reciprocal
+FLIC_HD double drcp(double a) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(a);
+#else
+    return 1.0 / a;
+#endif
+}
+FLIC_HD float d2f(double a) {
+#if defined(__CUDA_ARCH__)
+    return __double2float_rn(a);
+#else
+    return (float)a;
+#endif
+}
+FLIC_HD uint64_t f64_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u; memcpy(&u, &d, 8); return u;
+#endif
+}
+FLIC_HD double bits_f64(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+FLIC_HD uint32_t f32_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+
+// ---- glibc expf ---------------------------------------------------------------------------------
+// T[i] = bits(2^(i/32)) - (i << 47).  Published table of glibc's __exp2f_data (N = 32).
+#define FLIC_EXP2F_TABLE                                                                          \
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,   \
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,   \
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,   \
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,   \
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,   \
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,   \
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,   \
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull
+
+// `tab` points at the 32-entry table: shared memory on the device (each lane indexes its own
+// entry, so constant memory would serialise), a static array on the host.
+// The polynomial is evaluated with fused multiply-adds.  oracle/rans_oracle.c proves (exhaustive
+// sweep over |x| <= 104, tests/test_oracle_pinning.py) that fused and unfused evaluation both
+// agree with the host libm everywhere except two inputs deep inside part1's saturated range.
+FLIC_HD float expf_glibc(float x, const uint64_t* tab) {
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
+    const double Shift = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0;
+    const double C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0;
+    const double C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+    const uint32_t ux = f32_bits(x);
+    const uint32_t abstop = (ux >> 20) & 0x7ff;
+    if (abstop >= 0x42b) {  // |x| >= 88 or non-finite   (top12(88.0f) == 0x42b)
+        if (ux == 0xff800000u) return 0.0f;
+        if (abstop >= 0x7f8) return x + x;
+        if (x > 0x1.62e42ep6f) return INFINITY;
+        if (x < -0x1.9fe368p6f) return 0.0f;
+    }
+    const double xd = (double)x;
+    const double z = dmul(InvLn2N, xd);
+    double kd = dadd(z, Shift);
+    const uint64_t ki = f64_bits(kd);
+    kd = dsub(kd, Shift);
+    const double r = dsub(z, kd);
+    const uint64_t t = tab[ki & 31] + (ki << 47);
+    const double s = bits_f64(t);
+    const double zz = dfma(C0, r, C1);
+    const double r2 = dmul(r, r);
+    double y = dfma(C2, r, 1.0);
+    y = dfma(zz, r2, y);
+    y = dmul(y, s);
+    return d2f(y);
+}
+
+// ---- per-symbol model -----------------------------------------------------------------------------
+FLIC_HD int lower_of(float mean) {
+    // (int) round((double)mean * 256.0 - 1024.0), C round(): half away from zero
+    const double v = dsub(dmul((double)mean, 256.0), 1024.0);
+    return (int)round(v);
+}
+
+struct SymbolModel {
+    double mean_d;   // (double)mean
+    double scale_d;  // (double)scale
+    double rscale;   // RN(1 / scale_d)
+    int lower;       // window origin in 1/256 units
+    int32_t flags;   // ST_ZERO_SCALE / ST_NONFINITE
+};
+
+FLIC_HD SymbolModel make_model(float mean, float scale) {
+    SymbolModel m;
+    m.flags = 0;
+    if (scale == 0.0f) m.flags |= ST_ZERO_SCALE;
+    // |mean| is limited so that every window index stays below 2^23 and the float arithmetic of
+    // rans.pyx:33 (x - lower) is exact; 8-bit image latents are within a few units of zero.
+    if (!(fabsf(mean) <= 16384.0f) || !(fabsf(scale) < INFINITY)) m.flags |= ST_NONFINITE;
+    m.mean_d = (double)mean;
+    m.scale_d = (double)scale;
+    m.rscale = drcp(m.scale_d);
+    m.lower = (m.flags & ST_NONFINITE) ? 0 : lower_of(mean);
+    return m;
+}
+
+// Correctly rounded a / b from r = RN(1/b) (Markstein): q0 = RN(a r); e = a - b q0 (exact, fma);
+// q = RN(q0 + e r).  Valid here because b is a float widened to double (never an all-ones
+// significand), a and b are far from the double over/underflow thresholds, and r is the
+// correctly rounded reciprocal.  tests/ compares it with IEEE division on the host (millions of
+// cases) and on the device against __ddiv_rn.
+FLIC_HD double div_by_scale(double a, const SymbolModel& m) {
+    const double q0 = dmul(a, m.rscale);
+    const double e = dfma(-q0, m.scale_d, a);
+    return dfma(e, m.rscale, q0);
+}
+
+// part1 of CDF(s/256): (int) roundf( (float)( 1/(1+expf(-arg)) * 16775168 ) ),
+// arg = (float)( ((double)xq + 1/512 - mean) / scale ), xq = s/256 (exact in float).
+FLIC_HD int cdf_part1(int s, const SymbolModel& m, const uint64_t* tab) {
+    const double xq = (double)s * 0.00390625;  // exact
+    const double t4 = dsub(dadd(xq, 0.001953125), m.mean_d);
+    const float arg = d2f(div_by_scale(t4, m));
+    const float e = expf_glibc(-arg, tab);
+    const double p = drcp(dadd(1.0, (double)e));
+    const float prod = d2f(dmul(p, kPart1Scale));
+    return (int)roundf(prod);
+}
+
+// CDF(s/256) for integer symbol s.  part2 = round((xq - lower_f) * 256) + 1 = s - lower + 1
+// exactly when |s| and |lower| are below 2^24 (both floats exact, difference exact).
+FLIC_HD int cdf_at(int s, const SymbolModel& m, const uint64_t* tab) {
+    return cdf_part1(s, m, tab) + (s - m.lower + 1);
+}
+
+// Symbol value -> integer grid index; ok=false when x is not an exact multiple of 1/256 that the
+// window arithmetic represents exactly (then the reference's own result is garbage, App. D).
+FLIC_HD int symbol_index(float x, bool& ok) {
+    const float xs = x * 256.0f;
+    ok = fabsf(xs) < 8388608.0f;
+    const int s = ok ? (int)xs : 0;
+    ok = ok && ((float)s == xs);
+    return s;
+}
+
+struct SymbolTable {
+    uint32_t start;  // CDF(x - 1/256)
+    uint32_t freq;   // CDF(x) - start  (>= 1)
+};
+
+// encode pass 1 for one symbol (rans.pyx:50-56).  flags accumulates status bits.
+FLIC_HD SymbolTable make_table(float x, float mean, float scale, const uint64_t* tab, int32_t& flags) {
+    const SymbolModel m = make_model(mean, scale);
+    bool ok;
+    const int s = symbol_index(x, ok);
+    int32_t f = m.flags;
+    if (!ok || s < m.lower || s > m.lower + (kWindow - 1)) f |= ST_OUT_OF_WINDOW;
+    SymbolTable t;
+    if (f) {  // keep the coder alive with a harmless entry; the stream is reported as failed
+        t.start = 0; t.freq = 1;
+        flags |= f;
+        return t;
+    }
+    const int c0 = cdf_at(s - 1, m, tab);
+    const int c1 = cdf_at(s, m, tab);
+    t.start = (uint32_t)c0;
+    t.freq = (uint32_t)(c1 - c0);
+    return t;
+}
+
+// ---- rANS state machine ---------------------------------------------------------------------------
+// Encoder step (rans.pyx:62-65).  Returns true and sets `word` when a 32-bit word is emitted.
+// The 64-by-24-bit division uses a double reciprocal: after renormalisation
+// state < freq << 40, so q < 2^40 and the estimate is off by at most one; the integer fix-up
+// makes it exact.
+FLIC_HD bool rans_push(uint64_t& state, uint32_t start, uint32_t freq, uint32_t& word) {
+    bool emit = false;
+    if (state >= ((uint64_t)freq << 40)) {
+        word = (uint32_t)state;
+        state >>= 32;
+        emit = true;
+    }
+    const double rf = drcp((double)freq);
+    uint64_t q = (uint64_t)dmul((double)state, rf);
+    int64_t rem = (int64_t)(state - q * (uint64_t)freq);
+    if (rem < 0) { q -= 1; rem += freq; }
+    else if (rem >= (int64_t)freq) { q += 1; rem -= freq; }
+    state = (q << 24) + (uint64_t)rem + start;
+    return emit;
+}
+
+// Decoder: state update after the symbol is known (rans.pyx:108).
+FLIC_HD void rans_pop(uint64_t& state, uint32_t start, uint32_t freq) {
+    state = (state >> 24) * (uint64_t)freq + (state & kProbMask) - (uint64_t)start;
+}
+
+// ---- decoder symbol search ----------------------------------------------------------------------
+// First guess for "smallest s with CDF(s) > mod" from the continuous model
+//   g(s) = A sigmoid((s + 0.5 - 256 mean) / (256 scale)) + (s - lower + 1),  A = 16775168
+// solved for g = mod + 0.5 with two Newton steps in float.  Only speed depends on it.
+FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
+    const float A = 16775168.0f;
+    const float m = mean * 256.0f;
+    const float c = scale * 256.0f;
+    const float K = (m - (float)lower) - (float)mod;  // h(u) = A sig(u) + c u + K
+    float p0 = ((float)mod - 1024.0f) * (1.0f / A);
+    p0 = fminf(fmaxf(p0, 1e-7f), 1.0f - 1e-7f);
+#if defined(__CUDA_ARCH__)
+    float u = __logf(__fdividef(p0, 1.0f - p0));
+#else
+    float u = logf(p0 / (1.0f - p0));
+#endif
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#if defined(__CUDA_ARCH__)
+        const float e = __expf(-u);
+        const float sg = __fdividef(1.0f, 1.0f + e);
+#else
+        const float e = expf(-u);
+        const float sg = 1.0f / (1.0f + e);
+#endif
+        const float h = A * sg + c * u + K;
+        const float dh = A * sg * (1.0f - sg) + c;
+#if defined(__CUDA_ARCH__)
+        u -= __fdividef(h, dh);
+#else
+        u -= h / dh;
+#endif
+    }
+    const float sr = ceilf(m - 0.5f + c * u);
+    int g = lower + 1024;
+    if (fabsf(sr) < 1.0e9f) g = (int)sr;
+    g = g < lower ? lower : g;
+    g = g > lower + (kWindow - 1) ? lower + (kWindow - 1) : g;
+    return g;
+}
+
+// Bracketing search.  Invariant: CDF(lo) <= mod < CDF(hi), where lo = lower-1 and
+// hi = lower+2048 start as *virtual* ends exactly as in the reference's binary search
+// (rans.pyx:96-104 never evaluates outside the window, and treats the window's left edge as
+// "not greater").  Finishes when hi == lo + 1 with both CDF values evaluated, which are then
+// the (start, end) the reference recomputes at rans.pyx:106-107.  Any probe order returns the
+// reference's answer because CDF is non-decreasing in s.
+struct SearchState {
+    int lo, hi;        // bracket
+    int c_lo, c_hi;    // CDF values, -1 = not evaluated yet
+    int probe;         // next point to evaluate
+    int step;          // gallop step
+    bool done;
+};
+
+FLIC_HD SearchState search_begin(uint32_t mod, float mean, float scale, const SymbolModel& m) {
+    SearchState st;
+    st.lo = m.lower - 1;
+    st.hi = m.lower + kWindow;
+    st.c_lo = -1;
+    st.c_hi = -1;
+    st.step = 1;
+    st.done = false;
+    st.probe = guess_symbol(mod, mean, scale, m.lower);
+    return st;
+}
+
+// Feed CDF(st.probe) = c; choose the next probe or finish.
+FLIC_HD void search_feed(SearchState& st, int c, uint32_t mod) {
+    const bool greater = c > (int)mod;  // mod < 2^24; c < 0 (impossible in-window) reads as "not greater"
+    if (st.probe == st.lo) { st.c_lo = c; }
+    else if (st.probe == st.hi) { st.c_hi = c; }
+    else if (greater) { st.hi = st.probe; st.c_hi = c; }
+    else { st.lo = st.probe; st.c_lo = c; }
+
+    if (st.hi - st.lo == 1) {
+        if (st.c_hi < 0 && st.c_lo < 0) { st.probe = st.hi; return; }
+        if (st.c_lo < 0) { st.probe = st.lo; return; }
+        if (st.c_hi < 0) { st.probe = st.hi; return; }
+        st.done = true;
+        return;
+    }
+    if (st.c_lo >= 0 && st.c_hi >= 0) {  // both ends real: bisect
+        st.probe = st.lo + ((st.hi - st.lo) >> 1);
+        return;
+    }
+    // gallop away from the end that is known
+    if (st.c_hi >= 0) {  // answer is at or left of hi
+        int p = st.hi - st.step;
+        st.probe = p > st.lo ? p : st.lo + 1;
+    } else {             // answer is right of lo
+        int p = st.lo + st.step;
+        st.probe = p < st.hi ? p : st.hi - 1;
+    }
+    st.step <<= 2;
+}
+
+// One symbol.  Returns the integer grid index; updates state.
+FLIC_HD int decode_symbol(uint64_t& state, float mean, float scale,
+                                             const uint64_t* s_tab, int32_t& flags) {
+    const uint32_t mod = (uint32_t)state & kProbMask;
+    const SymbolModel m = make_model(mean, scale);
+    flags |= m.flags;
+    const int g = guess_symbol(mod, mean, scale, m.lower);
+    // the two evaluations are independent: the compiler interleaves them
+    int c_hi = cdf_at(g, m, s_tab);
+    int c_lo = cdf_at(g - 1, m, s_tab);
+    int s = g;
+    const bool left_ok = (g == m.lower) || (c_lo <= (int)mod);  // window's left edge is virtual
+    if (!(left_ok && c_hi > (int)mod)) {
+        // slow path: bracket from what is already known, then gallop / bisect
+        SearchState st;
+        st.lo = m.lower - 1; st.hi = m.lower + kWindow;
+        st.c_lo = -1; st.c_hi = -1; st.step = 2; st.done = false;
+        if (c_hi <= (int)mod) {  // answer is right of g
+            st.lo = g; st.c_lo = c_hi;
+            st.probe = g + 1 < st.hi ? g + 1 : st.hi;
+        } else {                 // c_lo > mod and g - 1 >= lower: answer is at or left of g - 1
+            st.hi = g - 1; st.c_hi = c_lo;
+            st.probe = g - 2 > st.lo ? g - 2 : st.lo;
+        }
+        while (!st.done) {
+            const int c = cdf_at(st.probe, m, s_tab);
+            search_feed(st, c, mod);
+        }
+        s = st.hi; c_hi = st.c_hi; c_lo = st.c_lo;
+        if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
+    }
+    rans_pop(state, (uint32_t)c_lo, (uint32_t)(c_hi - c_lo));
+    return s;
+}
+
+}  // namespace flic

@@ -1,0 +1,41 @@
+// flic_device.cuh -- device-only helpers shared by the kernels.
+#pragma once
+#include "flic_core.cuh"
+
+namespace flic {
+
+// glibc's exp2f table; each TU keeps its own 256-byte constant copy and stages it into shared
+// memory once per CTA (lanes index it divergently, which constant memory would serialise).
+static __constant__ uint64_t c_exp2f_tab[32] = {FLIC_EXP2F_TABLE};
+
+__device__ __forceinline__ void stage_exp_table(uint64_t* s_tab) {
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
+    __syncthreads();
+}
+
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+    int lo = __shfl_sync(0xffffffffu, (int)(uint32_t)(uint64_t)v, src);
+    int hi = __shfl_sync(0xffffffffu, (int)(uint32_t)((uint64_t)v >> 32), src);
+    return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
+}
+
+__device__ __forceinline__ int64_t warp_max_i64(int64_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int64_t o = shfl_i64(v, (threadIdx.x & 31) ^ d);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+inline int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace flic

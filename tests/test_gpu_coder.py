@@ -1,0 +1,183 @@
+"""GPU parity tests of the coder kernels, through the C ABI, against the CPU oracle.
+
+Bit-exact bar (BASELINE.json): frequency tables identical to the reference's quantisation;
+each stream's (final_state, words) identical to the reference coder run on the same slice;
+decoded symbols identical to the input.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _data import gen, ragged_offsets
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["test", "coder", "wide", "edges"]
+
+
+def _cuda(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def _u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cdf_tables_bit_exact(oracle, kind):
+    from flic_b200 import rans
+    n = 1 << 20
+    x, mean, scale = gen(kind, n, 11)
+    _, st_o, fr_o = oracle.tables(x, mean, scale)
+    xd, md, sd = _cuda(x, mean, scale)
+    start, freq, status = rans.cdf_tables(xd, md, sd)
+    assert int(status.item()) == 0
+    assert np.array_equal(_u32(start), st_o.astype(np.uint32))
+    assert np.array_equal(_u32(freq), fr_o.astype(np.uint32))
+    assert int(_u32(freq).min()) >= 1
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,n_streams", [(200_000, 1), (200_000, 37), (300_000, 1000), (50_000, 4097)])
+def test_streams_bit_exact_and_round_trip(oracle, kind, n, n_streams):
+    from flic_b200 import rans
+    x, mean, scale = gen(kind, n, 5 + n_streams)
+    off = ragged_offsets(n, n_streams, 99 + n_streams)
+    words_o, woff_o, states_o, status_o = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+    assert not status_o.any()
+    xd, md, sd = _cuda(x, mean, scale)
+    offd = torch.from_numpy(off).cuda()
+    enc = rans.encode_streams(xd, md, sd, offd)
+    assert not enc.status.any().item()
+    assert np.array_equal(enc.word_offsets.cpu().numpy(), woff_o)
+    assert np.array_equal(_u64(enc.final_states), states_o)
+    assert np.array_equal(_u32(enc.words), words_o)
+    # the reference's accounting: 64 bits per stream + 32 per word (trainer.py:326-327)
+    assert enc.bits() == 64 * n_streams + 32 * words_o.size
+    xr, end_states, status = rans.decode_streams(enc, md, sd, offd)
+    assert not status.any().item()
+    assert torch.equal(xr, xd)
+    assert bool((end_states == (1 << 32)).all().item())
+
+
+def test_uniform_partition_imagenet64_shape(oracle):
+    """Per image x level streams of the imagenet64 model: 6144 / 3072 / 3072 symbols (App. B)."""
+    from flic_b200 import rans
+    imgs = 24
+    for seg in (6144, 3072):
+        n = imgs * seg
+        x, mean, scale = gen("test", n, seg)
+        off = np.arange(imgs + 1, dtype=np.int64) * seg
+        words_o, woff_o, states_o, _ = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+        xd, md, sd = _cuda(x, mean, scale)
+        enc = rans.encode_streams(xd, md, sd, rans.uniform_offsets(imgs, seg, "cuda"))
+        assert np.array_equal(_u32(enc.words), words_o)
+        assert np.array_equal(_u64(enc.final_states), states_o)
+        xr, end, status = rans.decode_streams(enc, md, sd, torch.from_numpy(off).cuda())
+        assert torch.equal(xr, xd) and not status.any().item()
+
+
+def test_empty_and_tiny_inputs():
+    from flic_b200 import rans
+    e = torch.empty(0, dtype=torch.float32, device="cuda")
+    enc = rans.encode_streams(e, e, e, torch.zeros(1, dtype=torch.int64, device="cuda"))
+    assert enc.n_streams == 0 and enc.n_words() == 0
+    # streams that are all empty
+    enc = rans.encode_streams(e, e, e, torch.zeros(4, dtype=torch.int64, device="cuda"))
+    assert enc.n_streams == 3 and enc.n_words() == 0
+    assert bool((enc.final_states == (1 << 32)).all().item())
+    xr, end, status = rans.decode_streams(enc, e, e, torch.zeros(4, dtype=torch.int64, device="cuda"))
+    assert xr.numel() == 0 and not status.any().item()
+    # one symbol
+    x = torch.tensor([0.5], device="cuda")
+    m = torch.tensor([0.0], device="cuda")
+    s = torch.tensor([1.0], device="cuda")
+    enc = rans.encode_streams(x, m, s)
+    xr, end, status = rans.decode_streams(enc, m, s)
+    assert torch.equal(xr, x) and int(end.item()) == 1 << 32
+
+
+def test_kat8_known_answer():
+    """KAT-8 from the reference build (tests/golden/kat8.json)."""
+    import json
+    import os
+    from flic_b200 import rans
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat8.json")))
+    x, m, s = (torch.tensor(kat[k], dtype=torch.float32, device="cuda") for k in ("x", "mean", "scale"))
+    start, freq, status = rans.cdf_tables(x, m, s)
+    assert _u32(start).tolist() == kat["start"] and _u32(freq).tolist() == kat["freq"]
+    enc = rans.encode_streams(x, m, s)
+    assert int(_u64(enc.final_states)[0]) == kat["state"]
+    assert _u32(enc.words).tolist() == kat["buf"]
+
+
+def test_status_zero_scale_and_out_of_window():
+    from flic_b200 import rans, _lib
+    x = torch.tensor([0.5, 0.25, 100.0, 0.0], device="cuda")
+    m = torch.zeros(4, device="cuda")
+    s = torch.tensor([1.0, 0.0, 1.0, 1.0], device="cuda")
+    off = torch.tensor([0, 1, 2, 3, 4], device="cuda")
+    enc = rans.encode_streams(x, m, s, off)
+    st = enc.status.cpu().tolist()
+    assert st[0] == 0 and st[3] == 0
+    assert st[1] & _lib.ST_ZERO_SCALE
+    assert st[2] & _lib.ST_OUT_OF_WINDOW
+    with pytest.raises(ZeroDivisionError):
+        enc.check()
+    # off-grid symbol
+    enc = rans.encode_streams(torch.tensor([0.3], device="cuda"), m[:1], s[:1])
+    assert enc.status.cpu().tolist()[0] & _lib.ST_OUT_OF_WINDOW
+
+
+def test_truncated_stream_is_reported():
+    from flic_b200 import rans, _lib
+    x, mean, scale = gen("test", 5000, 3)
+    xd, md, sd = _cuda(x, mean, scale)
+    enc = rans.encode_streams(xd, md, sd)
+    nw = enc.n_words()
+    cut = rans.EncodedStreams(enc.words[: nw - 3].clone(), torch.tensor([0, nw - 3], device="cuda"),
+                              enc.final_states, enc.status, enc.n_symbols)
+    xr, end, status = rans.decode_streams(cut, md, sd)
+    assert status.cpu().tolist()[0] & (_lib.ST_UNDERRUN | _lib.ST_BAD_END_STATE | _lib.ST_NO_SYMBOL)
+
+
+def test_init_states_chain_like_coder_py(oracle):
+    """coder.Encode chains the state across levels (coder.py:25): encode(state_in) must accept any
+    state the previous call returned."""
+    from flic_b200 import rans
+    x, mean, scale = gen("coder", 4000, 8)
+    st1, buf1 = oracle.encode(1 << 32, 2000, x[:2000], mean[:2000], scale[:2000])
+    st2, buf2 = oracle.encode(st1, 2000, x[2000:], mean[2000:], scale[2000:])
+    xd, md, sd = _cuda(x[2000:], mean[2000:], scale[2000:])
+    init = torch.tensor([np.uint64(st1).astype(np.int64)], device="cuda")
+    enc = rans.encode_streams(xd, md, sd, None, init_states=init)
+    assert int(_u64(enc.final_states)[0]) == st2
+    assert np.array_equal(_u32(enc.words), buf2)
+
+
+def test_full_size_round_trip_properties():
+    """BASELINE config 5 chunk size (2048 images x 12288 symbols): size-independent properties --
+    decode(encode(x)) == x, every stream ends at 1<<32, bits match the word count."""
+    from flic_b200 import rans
+    imgs, per = 2048, 12288
+    n = imgs * per
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mean = torch.randint(-256, 257, (n,), device="cuda", generator=g).float() / 256
+    scale = torch.exp(10 * torch.rand(n, device="cuda", generator=g) - 5) / 256
+    x = torch.round((mean.double() + scale.double() * (10 * torch.rand(n, device="cuda", generator=g).double() - 5)) * 256) / 256
+    x = x.float()
+    # per image x level segments 6144 / 3072 / 3072
+    seg = torch.tensor([6144, 3072, 3072], device="cuda").repeat(imgs)
+    off = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), torch.cumsum(seg, 0)])
+    enc = rans.encode_streams(x, mean, scale, off)
+    assert not enc.status.any().item()
+    xr, end, status = rans.decode_streams(enc, mean, scale, off)
+    assert not status.any().item()
+    assert torch.equal(xr, x)
+    assert bool((end == (1 << 32)).all().item())
+    bps = enc.bits() / n
+    assert 4.2 < bps < 4.7  # rans/test.py distribution codes at ~4.4 bits/symbol
