@@ -81,6 +81,13 @@ int flic_cdf_tables(const float* x, const float* mean, const float* scale, int64
     return 0;
 }
 
+int flic_debug_expf(const float* x, float* y, int64_t n, flic_cuda_stream_t stream) {
+    if (n < 0 || (n > 0 && (!x || !y))) return fail(FLIC_E_ARG, "bad argument");
+    FLIC_CUDA(flic::launch_debug_expf(x, y, n, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
 int64_t flic_encode_workspace_bytes(int64_t n_symbols, int64_t n_streams) {
     return carve(nullptr, n_symbols, n_streams).bytes;
 }

@@ -27,6 +27,26 @@ cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
     if (flags) atomicOr(status_word, flags);
 }
 
+// Diagnostic: the device expf restatement on its own, so that tests can sweep it against the host
+// libm over the whole reachable domain.
+__global__ void __launch_bounds__(256)
+debug_expf_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    __shared__ uint64_t s_tab[32];
+    stage_exp_table(s_tab);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = expf_glibc(x[i], s_tab);
+}
+
+cudaError_t launch_debug_expf(const float* x, float* y, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    debug_expf_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cdf_tables(const float* x, const float* mean, const float* scale, int64_t n,
                               uint32_t* start, uint32_t* freq, int32_t* status_word,
                               cudaStream_t stream) {

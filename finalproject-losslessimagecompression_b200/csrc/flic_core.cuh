@@ -286,8 +286,13 @@ FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
     const float A = 16775168.0f;
     const float m = mean * 256.0f;
     const float c = scale * 256.0f;
-    const float K = (m - (float)lower) - (float)mod;  // h(u) = A sig(u) + c u + K
-    float p0 = ((float)mod - 1024.0f) * (1.0f / A);
+    // h(u) = A sig(u) + c u + (m - lower - mod), u = (s + 0.5 - m) / c.  In the upper half the
+    // constant A is folded into the integer (mod - A) and A sig(u) is written A - A (1 - sig(u)),
+    // so that every float term stays small and the residual keeps sub-bin precision in the tails.
+    const int mi = (int)mod;
+    const bool upper = mi > 8388608;
+    const float K = (m - (float)lower) - (float)(upper ? mi - 16775168 : mi);
+    float p0 = ((float)mi - 1024.0f) * (1.0f / A);
     p0 = fminf(fmaxf(p0, 1e-7f), 1.0f - 1e-7f);
 #if defined(__CUDA_ARCH__)
     float u = __logf(__fdividef(p0, 1.0f - p0));
@@ -297,14 +302,17 @@ FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
 #if defined(__CUDA_ARCH__)
-        const float e = __expf(-u);
-        const float sg = __fdividef(1.0f, 1.0f + e);
+        const float t = __expf(-fabsf(u));
+        const float r = __fdividef(1.0f, 1.0f + t);
 #else
-        const float e = expf(-u);
-        const float sg = 1.0f / (1.0f + e);
+        const float t = expf(-fabsf(u));
+        const float r = 1.0f / (1.0f + t);
 #endif
-        const float h = A * sg + c * u + K;
-        const float dh = A * sg * (1.0f - sg) + c;
+        const float big = r, small = t * r;          // sig(|u|), 1 - sig(|u|)
+        const float sg = u >= 0.0f ? big : small;    // sig(u)
+        const float cs = u >= 0.0f ? small : big;    // 1 - sig(u)
+        const float h = (upper ? -A * cs : A * sg) + c * u + K;
+        const float dh = A * big * small + c;
 #if defined(__CUDA_ARCH__)
         u -= __fdividef(h, dh);
 #else

@@ -17,6 +17,8 @@ cudaError_t launch_cdf_tables(const float* x, const float* mean, const float* sc
                               uint32_t* start, uint32_t* freq, int32_t* status_word,
                               cudaStream_t stream);
 
+cudaError_t launch_debug_expf(const float* x, float* y, int64_t n, cudaStream_t stream);
+
 // K1+K2 fused: per-stream rANS encode into worst-case scratch regions.
 //   scratch[offsets[s] .. offsets[s] + counts[s])  = words of stream s in emission order
 cudaError_t launch_rans_encode(const float* x, const float* mean, const float* scale,

@@ -1,0 +1,439 @@
+"""IDFlows / ConditionalFlows with real compress / decompress (reference: flows.py:24-181, 277-361).
+
+What is mirrored (same names, arguments and parameter layout, so the reference's YAML model
+blocks and checkpoints work unchanged):
+  IDFlows.__init__            flows.py:25-85     level structure, latents_shape
+  IDFlows.forward             flows.py:87-116    -> (latents, means, logscales, logv)
+  IDFlows.generated_from_*    flows.py:118-152
+  IDFlows.log_likelihood      flows.py:154-169   ideal code length (bits/dim oracle)
+  ConditionalFlows            flows.py:277-361   prior additionally sees a conditioning image
+What is new (the reference's IDFlows.encode / .decode are empty stubs, flows.py:177-181, and its
+only live call site, trainer.py:304-329, decodes with the means/logscales it already has):
+  compress(images_u8)   -> CompressedBatch      flow forward + prior + rANS encode, level by level
+  decompress(batch)     -> images_u8            decode last level, run the prior on what is known,
+                                                decode the next level, ... exactly the control flow
+                                                of generated_from_noise (flows.py:118-137)
+encode / decode are aliases of these.  Everything elementwise on this path is a CUDA kernel of
+libflic_b200.so; the DenseBlock convolutions are PyTorch fp32 (deterministic, TF32 off).
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+from copy import deepcopy
+
+import torch
+from torch import nn
+
+from . import _lib, rans
+from .container import CompressedBatch
+from .couplelib import AdditiveCouple, NNCouple
+from .distlib import NNDistribution
+from .extenddim import NNExtendDim
+from .invertible import InvertibleModuleList, Permute
+from .moduleregister import Register
+from .priorlib import NNPrior
+from .roundlib import NNRound
+
+
+class NNFlows(Register):
+    pass
+
+
+@contextlib.contextmanager
+def deterministic_convs():
+    """Compress and decompress must see bit-identical network outputs:
+    deterministic cuDNN algorithms, no autotuning, no TF32, and no gradient bookkeeping."""
+    cd, cb = torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark
+    t1, t2 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            yield
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = cd, cb
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = t1, t2
+
+
+def u8_to_grid(img: torch.Tensor) -> torch.Tensor:
+    """uint8 pixels -> the reference's input grid, rint(k/255*256)/256 (trainer.py:61,72)."""
+    if not img.is_cuda or img.dtype != torch.uint8:
+        raise TypeError("u8_to_grid expects a CUDA uint8 tensor")
+    img = img.contiguous()
+    out = torch.empty(img.shape, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().flic_u8_to_grid(img.data_ptr(), out.data_ptr(), img.numel(),
+                                              torch.cuda.current_stream(img.device).cuda_stream), "flic_u8_to_grid")
+    return out
+
+
+def grid_to_u8(x: torch.Tensor):
+    """Inverse of u8_to_grid; returns (uint8 tensor, status word tensor)."""
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    status = torch.zeros(1, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().flic_grid_to_u8(x.data_ptr(), out.data_ptr(), x.numel(), status.data_ptr(),
+                                              torch.cuda.current_stream(x.device).cuda_stream), "flic_grid_to_u8")
+    return out, status
+
+
+@NNFlows.register
+class IDFlows(nn.Module):
+    def __init__(self, nflows=8, nbits=8, nsplit=3, H=64, W=64, C=3, couple=None, extenddim=None, prior=None,
+                 distribution=None, round=None, batch_squeeze=0):
+        super().__init__()
+        if batch_squeeze:
+            raise NotImplementedError("batch_squeeze (flows.py:93-98) mixes images into one sample; not on the coding path")
+        couple, extenddim, prior = deepcopy(couple), deepcopy(extenddim), deepcopy(prior)
+        distribution, round = deepcopy(distribution), deepcopy(round)
+        self.nflows, self.nbits, self.nsplit = nflows, nbits, nsplit
+        self.C, self.H, self.W = C, H, W
+        self.batch_squeeze = 0
+        self.couple_type = NNCouple.get(couple.pop("name"))
+        self.prior_type = NNPrior.get(prior.pop("name"))
+        self.extenddim_type = NNExtendDim.get(extenddim.pop("name"))
+        self.dist_type = NNDistribution.get(distribution.pop("name"))
+        self.round_type = NNRound.get(round.pop("name"))
+        self._prior_cfg = deepcopy(prior)
+        self.blocks = nn.ModuleList()
+        self.latents_shape = []
+        channel, h, w = C, H, W
+        s = extenddim.get("scale")
+        for level in range(nsplit):
+            channel, h, w = channel * s * s, h // s, w // s
+            flow = InvertibleModuleList()
+            for _ in range(nflows):   # construction order = RNG order of flows.py:68-71
+                flow.append(Permute(dim=channel))
+                flow.append(self.couple_type(channel=channel, **deepcopy(couple)))
+            flow.append(Permute(dim=channel))
+            if level < nsplit - 1:
+                prior_nn = self.prior_type(channel // 2, channel - channel // 2, **deepcopy(prior))
+                self.latents_shape.append((channel // 2, h, w))
+                channel -= channel // 2
+            else:
+                prior_nn = self.prior_type(channel, 0, **deepcopy(prior))
+                self.latents_shape.append((channel, h, w))
+            self.blocks.append(nn.ModuleDict(dict(extend=self.extenddim_type(**deepcopy(extenddim)),
+                                                  flows=flow, prior=prior_nn)))
+        self.dist = self.dist_type(**distribution)
+        self.round = self.round_type(**round)
+
+    # ---- the reference's own entry points ------------------------------------------------------
+    def _prior_input(self, level, x_rest, cond):
+        """What block['prior'] is fed at this level (flows.py:106,112; ConditionalFlows :317,323)."""
+        return x_rest
+
+    def _flow_forward(self, block, x):
+        for m in block["flows"]:
+            if isinstance(m, AdditiveCouple):
+                x, _ = m.forward(x, None, inplace=True)   # x is the fresh output of the Permute before it
+            else:
+                x, _ = m.forward(x, None)
+        return x
+
+    def _flow_backward(self, block, x):
+        mods = list(block["flows"])
+        fresh = False
+        for m in reversed(mods):
+            if isinstance(m, AdditiveCouple):
+                x = m.backward(x, inplace=fresh)
+            else:
+                x = m.backward(x)
+                fresh = True
+        return x
+
+    @torch.no_grad()
+    def forward(self, x, logv=None, cond=None):
+        latents, means, logscales = [], [], []
+        for level in range(self.nsplit):
+            block = self.blocks[level]
+            x, _ = block["extend"](x, None)
+            cond = self._cond_step(level, cond)
+            x = self._flow_forward(block, x)
+            if level < self.nsplit - 1:
+                half = x.shape[1] // 2
+                z, x = x[:, :half], x[:, half:]
+                mean, logscale = block["prior"](self._prior_input(level, x, cond))
+            else:
+                z = x
+                mean, logscale = block["prior"](self._prior_input(level, x, cond))
+            latents.append(z)
+            means.append(mean)
+            logscales.append(logscale)
+        return latents, means, logscales, logv
+
+    def _cond_step(self, level, cond):
+        return cond
+
+    @torch.no_grad()
+    def generated_from_latents(self, latents):
+        x = None
+        for level in reversed(range(self.nsplit)):
+            block = self.blocks[level]
+            z = latents[level]
+            x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
+            x = self._flow_backward(block, x.contiguous())
+            x = block["extend"].backward(x)
+        return x
+
+    @torch.no_grad()
+    def generated_from_noise(self, latents):
+        x = None
+        for level in reversed(range(self.nsplit)):
+            block = self.blocks[level]
+            z = latents[level]
+            mean, logscale = block["prior"](x if level < self.nsplit - 1 else z)
+            z = self.round(z * torch.exp(logscale) + mean)
+            x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
+            x = self._flow_backward(block, x.contiguous())
+            x = block["extend"].backward(x)
+        return x
+
+    def log_likelihood(self, latents, means, logscales):
+        log_Ps = []
+        log_prob = torch.zeros(latents[0].shape[0], device=latents[0].device)
+        for z, mean, logscale in zip(latents, means, logscales):
+            logp = self.dist.log_prob(z, mean, logscale, self.nbits)
+            log_Ps.append(torch.mean(logp, dim=(1, 2, 3)))
+            log_prob = log_prob + torch.sum(logp, dim=(1, 2, 3))
+        return log_prob / (self.H * self.W * self.C), log_Ps
+
+    def inverse(self):
+        for block in self.blocks:
+            block["extend"].inverse()
+            block["flows"].inverse()
+
+    # ---- compress / decompress -------------------------------------------------------------------
+    def _segment_offsets(self, level: int, n_img: int, streams_per_segment: int, device):
+        """Stream partition of one level of one chunk.  A level's symbols are the row-major
+        flattening of (B, C_z, H, W) (trainer.py:311), image b owning a contiguous segment.
+        streams_per_segment k >= 1: each image segment is cut into k near-equal streams;
+        0: the reference's native partition, one stream for the whole level of the chunk."""
+        c, h, w = self.latents_shape[level]
+        seg = c * h * w
+        if streams_per_segment == 0:
+            return torch.tensor([0, n_img * seg], dtype=torch.int64, device=device)
+        k = streams_per_segment
+        cuts = torch.tensor([seg * j // k for j in range(k)], dtype=torch.int64, device=device)
+        base = torch.arange(n_img, dtype=torch.int64, device=device) * seg
+        off = (base[:, None] + cuts[None, :]).reshape(-1)
+        return torch.cat([off, torch.tensor([n_img * seg], dtype=torch.int64, device=device)])
+
+    def _chunk_forward(self, x, cond, n_real, sps, stats):
+        """x: (codec_batch, C, H, W) grid floats -> list of EncodedStreams, one per level."""
+        out = []
+        for level in range(self.nsplit):
+            block = self.blocks[level]
+            x, _ = block["extend"](x, None)
+            cond = self._cond_step(level, cond)
+            x = self._flow_forward(block, x)
+            if level < self.nsplit - 1:
+                half = x.shape[1] // 2
+                z, rest = x[:, :half].contiguous(), x[:, half:].contiguous()
+                mean, logscale = block["prior"](self._prior_input(level, rest, cond))
+                x = rest
+            else:
+                z = x
+                mean, logscale = block["prior"](self._prior_input(level, x, cond))
+            mean, scale = mean.contiguous(), torch.exp(logscale.contiguous())
+            if stats is not None:
+                stats.append((z, mean, logscale))
+            off = self._segment_offsets(level, n_real, sps, x.device)
+            n = int(n_real * math.prod(self.latents_shape[level]))
+            out.append(rans.encode_streams(z.reshape(-1)[:n], mean.reshape(-1)[:n], scale.reshape(-1)[:n], off))
+        return out
+
+    def compress(self, images: torch.Tensor, cond: torch.Tensor | None = None, codec_batch: int | None = None,
+                 streams_per_segment: int = 1, check: bool = True, stats: list | None = None) -> CompressedBatch:
+        """Lossless compression of uint8 images (N, C, H, W) on the GPU.
+
+        codec_batch: images per network pass (default: all of them).  It is recorded in the
+        result because the decoder has to run the networks on batches of the same shape to get
+        bit-identical prior outputs; the last chunk is padded with zero images whose streams are
+        not stored.  streams_per_segment: rANS streams per (image, level); 0 selects the
+        reference's native partition (one stream per level per chunk, trainer.py:308-315)."""
+        if images.dtype != torch.uint8 or images.dim() != 4:
+            raise TypeError("images must be uint8 (N, C, H, W)")
+        if tuple(images.shape[1:]) != (self.C, self.H, self.W):
+            raise ValueError(f"model codes {(self.C, self.H, self.W)} images, got {tuple(images.shape[1:])}")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.FlicError("compress needs the model on a CUDA device (no CPU fallback)")
+        images = images.to(dev, non_blocking=True)
+        n = images.shape[0]
+        cbs = int(codec_batch or max(n, 1))
+        batch = CompressedBatch(n, (self.C, self.H, self.W), self.nsplit, cbs, int(streams_per_segment))
+        with deterministic_convs(), torch.cuda.device(dev):
+            for i0 in range(0, n, cbs):
+                chunk = images[i0:i0 + cbs]
+                n_real = chunk.shape[0]
+                x = u8_to_grid(chunk)
+                c = None if cond is None else cond[i0:i0 + cbs].to(dev)
+                if n_real < cbs:
+                    x = torch.cat([x, x.new_zeros((cbs - n_real,) + tuple(x.shape[1:]))])
+                    if c is not None:
+                        c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
+                batch.sections.append(self._chunk_forward(x, c, n_real, int(streams_per_segment), stats))
+        if check:
+            for ch in batch.sections:
+                for e in ch:
+                    e.check()
+        return batch
+
+    def decompress(self, batch, cond: torch.Tensor | None = None, check: bool = True) -> torch.Tensor:
+        """Inverse of compress: CompressedBatch (or its bytes) -> uint8 images (N, C, H, W)."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.FlicError("decompress needs the model on a CUDA device (no CPU fallback)")
+        if isinstance(batch, (bytes, bytearray, memoryview)):
+            batch = CompressedBatch.from_bytes(bytes(batch), dev)
+        if tuple(batch.shape) != (self.C, self.H, self.W) or batch.n_levels != self.nsplit:
+            raise ValueError("container does not match this model")
+        n, cbs, sps = batch.n_images, batch.codec_batch, batch.streams_per_segment
+        outs, statuses = [], []
+        with deterministic_convs(), torch.cuda.device(dev):
+            for ci, i0 in enumerate(range(0, n, cbs)):
+                n_real = min(cbs, n - i0)
+                c = None if cond is None else cond[i0:i0 + cbs].to(dev)
+                if c is not None and n_real < cbs:
+                    c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
+                conds = self._cond_pyramid(c)
+                x = None
+                for level in reversed(range(self.nsplit)):
+                    block = self.blocks[level]
+                    cz, h, w = self.latents_shape[level]
+                    if level == self.nsplit - 1:
+                        probe = torch.zeros((cbs, cz, h, w), dtype=torch.float32, device=dev)
+                        mean, logscale = block["prior"](self._prior_input(level, probe, conds[level]))
+                    else:
+                        mean, logscale = block["prior"](self._prior_input(level, x, conds[level]))
+                    mean, scale = mean.contiguous(), torch.exp(logscale.contiguous())
+                    nsym = n_real * cz * h * w
+                    off = self._segment_offsets(level, n_real, sps, dev)
+                    z = torch.zeros((cbs, cz, h, w), dtype=torch.float32, device=dev)
+                    _, _, st = rans.decode_streams(batch.sections[ci][level], mean.reshape(-1)[:nsym],
+                                                   scale.reshape(-1)[:nsym], off, out=z.view(-1)[:nsym])
+                    statuses.append(st)
+                    x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
+                    x = self._flow_backward(block, x)
+                    x = block["extend"].backward(x)
+                img, st8 = grid_to_u8(x[:n_real])
+                statuses.append(st8)
+                outs.append(img)
+        if check:
+            for st in statuses:
+                rans.check_status(st)
+        return torch.cat(outs) if outs else torch.empty((0, self.C, self.H, self.W), dtype=torch.uint8, device=dev)
+
+    def _cond_pyramid(self, cond):
+        return [None] * self.nsplit
+
+    # the reference's stubs (flows.py:177-181), now real
+    def encode(self, x, **kw):
+        return self.compress(x, **kw)
+
+    def decode(self, x, **kw):
+        return self.decompress(x, **kw)
+
+
+@NNFlows.register
+class ConditionalFlows(IDFlows):
+    """IDFlows whose priors also see a conditioning image `cond` (e.g. a VQ-VAE reconstruction,
+    trainer.py:606-621), squeezed alongside x (flows.py:311) or passed through strided convs
+    (flows.py:313).  The coder is unchanged; only the prior's input grows by `ch` channels."""
+
+    def __init__(self, conv_for_cond=False, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.conv_for_cond = conv_for_cond
+        if conv_for_cond:
+            self.convs = nn.ModuleList()
+        ch = self.C
+        for level in range(self.nsplit):
+            block = self.blocks[level]
+            s = block["extend"].scale
+            ch *= s * s
+            old = block["prior"]
+            block["prior"] = self.prior_type(
+                old.out_channel, (old.cond_channel if old.cond_channel > 0 else old.out_channel) + ch,
+                **deepcopy(self._prior_cfg))
+            if conv_for_cond:
+                self.convs.append(nn.Conv2d(ch // s // s, ch, 4, 2, 1))
+
+    def _cond_step(self, level, cond):
+        if cond is None:
+            raise ValueError("ConditionalFlows needs cond")
+        if self.conv_for_cond:
+            return self.convs[level](cond)
+        return self.blocks[level]["extend"](cond, None)[0]
+
+    def _prior_input(self, level, x_rest, cond):
+        if level == self.nsplit - 1:
+            x_rest = torch.zeros_like(x_rest)        # flows.py:323
+        return torch.cat((x_rest, cond), dim=1)
+
+    def _cond_pyramid(self, cond):
+        out = []
+        for level in range(self.nsplit):
+            cond = self._cond_step(level, cond)
+            out.append(cond)
+        return out
+
+    @torch.no_grad()
+    def generated_from_noise(self, latents, cond):
+        conds = self._cond_pyramid(cond)
+        x = None
+        for level in reversed(range(self.nsplit)):
+            block = self.blocks[level]
+            z = latents[level]
+            mean, logscale = block["prior"](self._prior_input(level, x if level < self.nsplit - 1 else z, conds[level]))
+            z = self.round(z * torch.exp(logscale) + mean)
+            x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
+            x = self._flow_backward(block, x.contiguous())
+            x = block["extend"].backward(x)
+        return x
+
+
+def build_model(cfg: dict) -> nn.Module:
+    """`train.model` block of a reference YAML config -> model (trainer.py:204)."""
+    cfg = deepcopy(cfg)
+    cfg.pop("load_path", None)
+    return NNFlows.get(cfg.pop("name"))(**cfg)
+
+
+def perturb_heads(model: nn.Module, std: float = 0.02, seed: int = 0) -> None:
+    """The DenseBlock heads are zero-initialised (nnblock.py:50-51), which makes every coupling
+    the identity and every prior mean=0, scale=1.  For tests and benchmarks on random-init
+    models, re-draw them N(0, std) in module order (KAT-flow)."""
+    from .nnblock import DenseBlock
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, DenseBlock):
+                head = m.layers[-1]
+                head.weight.copy_(torch.randn(head.weight.shape, generator=g) * std)
+                head.bias.copy_(torch.randn(head.bias.shape, generator=g) * std)
+
+
+def smoke_round_trip() -> None:
+    """Tiny IDFlows on cuda:0: compress -> bytes -> decompress must return the pixels."""
+    import random
+    torch.manual_seed(0)
+    random.seed(0)
+    layer = dict(name="DenseLayer", act="LeakyReLU")
+    cfg = dict(name="IDFlows", nflows=2, nbits=8, nsplit=2, H=16, W=16, C=3,
+               couple=dict(name="AdditiveCouple", split=0.75, round=dict(name="Round", nbits=8),
+                           nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=layer)),
+               extenddim=dict(name="ExtendDim", scale=2),
+               prior=dict(name="Prior", round=dict(name="Round", nbits=8),
+                          nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=layer)),
+               distribution=dict(name="DLogistic"), round=dict(name="Round", nbits=8))
+    model = build_model(cfg)
+    perturb_heads(model, 0.02)
+    model = model.cuda().eval()
+    img = torch.randint(0, 256, (5, 3, 16, 16), dtype=torch.uint8, generator=torch.Generator().manual_seed(1)).cuda()
+    blob = model.compress(img, codec_batch=4).to_bytes()
+    rec = model.decompress(blob)
+    assert torch.equal(rec, img), "flow round trip is not lossless"

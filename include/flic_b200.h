@@ -66,6 +66,10 @@ int flic_cdf_tables(const float* x, const float* mean, const float* scale, int64
                     uint32_t* start, uint32_t* freq, int32_t* status_word,
                     flic_cuda_stream_t stream);
 
+/* Diagnostic.  y[i] = the device restatement of glibc expf (the `exp` of rans/rans.pyx:26 as the
+ * reference links it, expf@GLIBC_2.27, rans/rans.cpp:1301).  Lets a test sweep it against libm. */
+int flic_debug_expf(const float* x, float* y, int64_t n, flic_cuda_stream_t stream);
+
 /* Bytes of device workspace flic_rans_encode needs (worst-case word scratch + scan temporaries). */
 int64_t flic_encode_workspace_bytes(int64_t n_symbols, int64_t n_streams);
 

@@ -42,6 +42,8 @@ def lib() -> C.CDLL:
         L.flic_oracle_expf_host.argtypes = [C.c_float]
         L.flic_oracle_expf_sweep.restype = C.c_uint64
         L.flic_oracle_expf_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_int, u32p, C.c_uint32]
+        L.flic_oracle_expf_compare.restype = None
+        L.flic_oracle_expf_compare.argtypes = [C.c_uint32, C.c_int64, f32p, u64p, u64p, u32p, C.c_uint32]
         L.flic_oracle_cdf.restype = C.c_int
         L.flic_oracle_cdf.argtypes = [C.c_float] * 4
         L.flic_oracle_lower.restype = C.c_int
@@ -170,6 +172,17 @@ def expf_sweep(lo_bits: int, hi_bits: int, fma: bool = False, max_bad: int = 16)
     bad = np.zeros(max_bad, np.uint32)
     n = lib().flic_oracle_expf_sweep(lo_bits, hi_bits, int(fma), _p(bad, C.c_uint32), max_bad)
     return int(n), bad[: min(int(n), max_bad)].copy()
+
+
+def expf_compare(lo_bits: int, got: np.ndarray, max_bad: int = 16):
+    """got[i] = candidate expf of the float with bit pattern lo_bits+i.
+    Returns (mismatches vs host libm, mismatches vs the restatement, first bad bit patterns)."""
+    got = np.ascontiguousarray(got, dtype=np.float32)
+    bh, br = C.c_uint64(0), C.c_uint64(0)
+    bad = np.zeros(max_bad, np.uint32)
+    lib().flic_oracle_expf_compare(lo_bits, got.size, _p(got, C.c_float), C.byref(bh), C.byref(br),
+                                   _p(bad, C.c_uint32), max_bad)
+    return int(bh.value), int(br.value), bad[: min(int(bh.value), max_bad)].copy()
 
 
 # ---- the reference's own Cython module, rebuilt (oracle/_ref) -------------------------------

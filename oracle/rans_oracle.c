@@ -124,6 +124,27 @@ uint64_t flic_oracle_expf_sweep(uint32_t lo_bits, uint32_t hi_bits, int use_fma,
     return bad;
 }
 
+/* got[i] is some implementation's expf(float with bit pattern lo_bits + i); count disagreements
+ * with the host libm and with the restatement. */
+void flic_oracle_expf_compare(uint32_t lo_bits, int64_t n, const float *got, uint64_t *bad_vs_host,
+                              uint64_t *bad_vs_restated, uint32_t *first_bad, uint32_t max_bad)
+{
+    uint64_t bh = 0, br = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t u = lo_bits + (uint32_t)i;
+        float x;
+        memcpy(&x, &u, 4);
+        uint32_t g = as_u32(got[i]);
+        if (g != as_u32(expf(x))) {
+            if (bh < max_bad) first_bad[bh] = u;
+            ++bh;
+        }
+        if (g != as_u32(expf_restated_impl(x, 1))) ++br;
+    }
+    *bad_vs_host = bh;
+    *bad_vs_restated = br;
+}
+
 /* ---- logistic / CDF (rans/rans.pyx:25-35 with rans.cpp promotions) ------------ */
 
 /* rans.cpp:1301-1306: argument float32, expf float32, sum and divide in double. */

@@ -10,6 +10,12 @@
 import numpy as np
 
 
+def c_round(v):
+    """C round(): half away from zero (numpy's round is half to even)."""
+    v = np.asarray(v, np.float64)
+    return np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5))
+
+
 def gen(kind: str, n: int, seed: int):
     rng = np.random.default_rng(seed)
     if kind == "test":
@@ -25,13 +31,12 @@ def gen(kind: str, n: int, seed: int):
         scale = np.exp(rng.uniform(-12, 4, n)).astype(np.float32)
         u = rng.random(n)
         x = np.round((mean.astype(np.float64) + scale.astype(np.float64) * np.log(u / (1 - u))) * 256) / 256
-        lo = np.round(mean.astype(np.float64) * 256 - 1024)
+        lo = c_round(mean.astype(np.float64) * 256 - 1024)
         x = np.clip(x * 256, lo, lo + 2047) / 256
     elif kind == "edges":
         mean = rng.normal(0, 3.0, n).astype(np.float32)
         scale = np.exp(rng.uniform(-3, 3, n)).astype(np.float32)
-        v = mean.astype(np.float64) * 256 - 1024
-        lo = np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5))  # C round(): half away from zero
+        lo = c_round(mean.astype(np.float64) * 256 - 1024)
         pick = rng.integers(0, 4, n)
         x = np.where(pick == 0, lo, np.where(pick == 1, lo + 2047, np.where(pick == 2, lo + 1, lo + 2046))) / 256
     else:

@@ -23,6 +23,8 @@ int hh_cdf(int s, float mean, float scale) {
     return cdf_at(s, m, kTab);
 }
 
+int hh_guess(uint32_t mod, float mean, float scale) { return guess_symbol(mod, mean, scale, lower_of(mean)); }
+
 int hh_tables(const float* x, const float* mean, const float* scale, int64_t n, uint32_t* start,
               uint32_t* freq) {
     int32_t flags = 0;
