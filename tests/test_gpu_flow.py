@@ -279,22 +279,45 @@ def test_drop_in_matches_reference_goldens_like_rans_test_py():
 
 
 def test_coder_wrappers_chain_state_like_coder_py(oracle):
+    """coder.Encode / Decode chain the rANS state from level to level (coder.py:25,36).  The
+    reference's chain only decodes correctly when the first symbol of every later level does not
+    push a word; level 1 therefore starts with a near-certain symbol
+    (freq ~ 2^24, so freq << 40 can never be reached).  The buggy case is checked to be
+    *reported* rather than silently mis-decoded."""
     from flic_b200 import coder
     g = torch.Generator().manual_seed(3)
     shapes = [(2, 6, 8, 8), (2, 24, 4, 4)]
-    means = [torch.randint(-32, 33, s, generator=g).float().div(256).cuda() for s in shapes]
-    logscales = [(torch.rand(s, generator=g) * 0.01 - 0.005).cuda() for s in shapes]
-    lat = [(torch.round((m.cpu() + torch.exp(l.cpu()) * (torch.rand(m.shape, generator=g) - 0.5)) * 256) / 256).cuda()
+    means = [torch.randint(-32, 33, s, generator=g).float().div(256) for s in shapes]
+    logscales = [(torch.rand(s, generator=g) * 0.01 - 0.005) for s in shapes]
+    lat = [torch.round((m + torch.exp(l) * (torch.rand(m.shape, generator=g) - 0.5)) * 256) / 256
            for m, l in zip(means, logscales)]
+    logscales[1].view(-1)[0] = -20.0
+    lat[1].view(-1)[0] = means[1].view(-1)[0]
+    means, logscales, lat = ([t.cuda() for t in ts] for ts in (means, logscales, lat))
     x, buffers = coder.Encode(lat, means, logscales)
     st = 1 << 32
+    scales = [torch.exp(l).reshape(-1).cpu().numpy() for l in logscales]
     for i in range(2):                                  # coder.py:18-27 with the oracle as rans
-        scale = torch.exp(logscales[i]).reshape(-1).cpu().numpy()
-        st, buf = oracle.encode(st, lat[i].numel(), lat[i].reshape(-1).cpu().numpy(), means[i].reshape(-1).cpu().numpy(), scale)
+        st, buf = oracle.encode(st, lat[i].numel(), lat[i].reshape(-1).cpu().numpy(),
+                                means[i].reshape(-1).cpu().numpy(), scales[i])
         assert buffers[i] == buf.tolist()
     assert x == st
     x2, rec = coder.Decode(buffers, means, logscales, x)
-    assert all(torch.equal(a, b) for a, b in zip(rec, lat))
+    assert x2 == 1 << 32 and all(torch.equal(a, b) for a, b in zip(rec, lat))
+    so = x
+    for i in (1, 0):                                    # coder.py:29-38 with the oracle as rans
+        so, msg = oracle.decode(so, np.asarray(buffers[i], np.uint32)[::-1], lat[i].numel(),
+                                means[i].reshape(-1).cpu().numpy()[::-1], scales[i][::-1])
+        assert np.array_equal(msg[::-1], lat[i].reshape(-1).cpu().numpy())
+    assert so == x2
+    # the reference's latent bug: make level 1's first symbol push a word -> its chain cannot be decoded
+    logscales[1].view(-1)[0] = 0.0
+    x, buffers = coder.Encode(lat, means, logscales)
+    try:
+        _, rec = coder.Decode(buffers, means, logscales, x)
+        assert not all(torch.equal(a, b) for a, b in zip(rec, lat))
+    except ValueError:
+        pass
 
 
 def test_host_codec_c_abi_with_host_buffers(oracle):
