@@ -13,6 +13,10 @@ __device__ __forceinline__ void stage_exp_table(uint64_t* s_tab) {
     __syncthreads();
 }
 
+// CTA-wide barrier that may be reached from different code paths of a warp-specialised kernel
+// (every thread of the CTA executes the same NUMBER of barriers; bar.sync counts arrivals).
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
 __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
     int lo = __shfl_sync(0xffffffffu, (int)(uint32_t)(uint64_t)v, src);
     int hi = __shfl_sync(0xffffffffu, (int)(uint32_t)((uint64_t)v >> 32), src);

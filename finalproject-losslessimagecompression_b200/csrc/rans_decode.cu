@@ -14,13 +14,20 @@
 // On the reference's own test distributions that is 2.00 exact CDF evaluations per symbol
 // instead of 13-14; a galloping / bisecting bracket takes over when the guess is off.
 //
-// Mapping: as in the encoder, one lane per stream and a warp-wide [32 streams][32 symbols] tile
-// of (mean, scale) staged through shared memory with coalesced 128-byte rows; decoded symbols go
-// back through the same tile so the x store is coalesced too.
+// Mapping: one lane per stream (every CDF evaluation depends on the stream's current state, so
+// unlike the encoder nothing can be hoisted to helper warps); a warp stages a
+// [32 streams][16 symbols] tile of (mean, scale) through shared memory with coalesced 64-byte
+// row segments, and the decoded symbols go back through the same tile so the x store is
+// coalesced too.
 #include "flic_device.cuh"
 #include "flic_kernels.cuh"
 
 namespace flic {
+
+// Symbols per stream per tile.  16 keeps the tile at 4.3 KB per warp, so that registers (not
+// shared memory) limit residency: 32 warps per SM.
+constexpr int kDecTile = 16;
+constexpr int kRowsPerPass = kLanes / kDecTile;  // rows staged per warp-wide load
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -30,7 +37,7 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
                    int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
                    int32_t* __restrict__ status, int check_end) {
     __shared__ uint64_t s_tab[32];
-    __shared__ float2 s_tile[WARPS][kLanes][kTile + 1];
+    __shared__ float2 s_tile[WARPS][kLanes][kDecTile + 1];
     stage_exp_table(s_tab);
 
     const int lane = threadIdx.x & 31;
@@ -47,25 +54,28 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
     int64_t wpos = live ? word_offsets[stream + 1] : 0;  // one past the last unread word
     uint64_t state = live ? states[stream] : kRansL;
     int32_t flags = 0;
-    float2(*tile)[kTile + 1] = s_tile[warp];
+    float2(*tile)[kDecTile + 1] = s_tile[warp];
+    const int sub = lane / kDecTile;   // which of the rows of a pass this lane helps with
+    const int col = lane % kDecTile;   // symbol within the tile row
 
-    const int64_t n_tiles = (max_len + kTile - 1) / kTile;
+    const int64_t n_tiles = (max_len + kDecTile - 1) / kDecTile;
     for (int64_t t = n_tiles - 1; t >= 0; --t) {
-        const int64_t t0 = t * kTile;
-        // ---- phase A: stage (mean, scale) of the tile, coalesced rows
+        const int64_t t0 = t * kDecTile;
+        // ---- phase A: stage (mean, scale) of the tile; each half-warp loads one 64-byte row
 #pragma unroll 4
-        for (int r = 0; r < kLanes; ++r) {
+        for (int p = 0; p < kLanes / kRowsPerPass; ++p) {
+            const int r = p * kRowsPerPass + sub;
             const int64_t b_r = shfl_i64(beg, r);
             const int64_t l_r = shfl_i64(len, r);
-            const int64_t i = t0 + lane;
-            if (i < l_r) tile[r][lane] = make_float2(__ldg(mean + b_r + i), __ldg(scale + b_r + i));
+            const int64_t i = t0 + col;
+            if (i < l_r) tile[r][col] = make_float2(__ldg(mean + b_r + i), __ldg(scale + b_r + i));
         }
         __syncwarp();
         // ---- phase B: lane-per-stream, last symbol of the tile first
         const int64_t rem = len - t0;
-        const int cnt = rem >= kTile ? kTile : (rem > 0 ? (int)rem : 0);
+        const int cnt = rem >= kDecTile ? kDecTile : (rem > 0 ? (int)rem : 0);
 #pragma unroll 1
-        for (int j = kTile - 1; j >= 0; --j) {
+        for (int j = kDecTile - 1; j >= 0; --j) {
             if (j < cnt) {
                 if (state < kRansL) {  // rans.pyx:87-89
                     if (wpos > wbeg) state = (state << 32) | __ldg(packed + (--wpos));
@@ -79,11 +89,12 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
         __syncwarp();
         // ---- phase C: coalesced store of the decoded symbols
 #pragma unroll 4
-        for (int r = 0; r < kLanes; ++r) {
+        for (int p = 0; p < kLanes / kRowsPerPass; ++p) {
+            const int r = p * kRowsPerPass + sub;
             const int64_t b_r = shfl_i64(beg, r);
             const int64_t l_r = shfl_i64(len, r);
-            const int64_t i = t0 + lane;
-            if (i < l_r) x_out[b_r + i] = tile[r][lane].x;
+            const int64_t i = t0 + col;
+            if (i < l_r) x_out[b_r + i] = tile[r][col].x;
         }
         __syncwarp();
     }
@@ -101,7 +112,7 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
                                cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
     const int64_t warps = (n_streams + kLanes - 1) / kLanes;
-    if (warps <= (int64_t)sm_count() * 8) {
+    if (warps <= (int64_t)sm_count() * 16) {
         rans_decode_kernel<1><<<(unsigned)warps, 32, 0, stream>>>(
             packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end);
     } else {

@@ -16,6 +16,15 @@ extern "C" {
 
 float hh_expf(float x) { return expf_glibc(x, kTab); }
 
+void hh_expf_array(uint32_t lo_bits, int64_t n, float* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t u = lo_bits + (uint32_t)i;
+        float x;
+        memcpy(&x, &u, 4);
+        out[i] = expf_glibc(x, kTab);
+    }
+}
+
 int hh_lower(float mean) { return lower_of(mean); }
 
 int hh_cdf(int s, float mean, float scale) {

@@ -25,8 +25,13 @@ imgs = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 per = 12288
 n = imgs * per
 x, mean, scale = synth(n)
-for name, seg in (("per image x level (6144/3072/3072)", [6144, 3072, 3072]), ("per image (12288)", [12288]), ("768-symbol streams", [768])):
-    segs = torch.tensor(seg, device="cuda").repeat(n // sum(seg))
+def level_major(imgs, segs):
+    return torch.cat([torch.full((imgs,), sg, device="cuda") for sg in segs])
+cases = (("level-major 6144/3072/3072", level_major(imgs, [6144, 3072, 3072])),
+         ("equal 3072 (4/image)", torch.full((n // 3072,), 3072, device="cuda")),
+         ("per image (12288)", torch.full((imgs,), 12288, device="cuda")),
+         ("768-symbol streams", torch.full((n // 768,), 768, device="cuda")))
+for name, segs in cases:
     off = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), torch.cumsum(segs, 0)])
     ws = rans.Workspace()
     enc = rans.encode_streams(x, mean, scale, off, workspace=ws)
