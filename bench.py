@@ -511,7 +511,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="flic", choices=["flic", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "full"])
-    ap.add_argument("--images", type=int, default=32768, help="images per step per GPU (sweep)")
+    ap.add_argument("--images", type=int, default=65536, help="images per step per GPU (sweep)")
     ap.add_argument("--e2e-images", type=int, default=8192)
     ap.add_argument("--batch", type=int, default=256, help="images per step per GPU (full)")
     ap.add_argument("--codec-batch", type=int, default=64)

@@ -15,19 +15,30 @@
 // instead of 13-14; a galloping / bisecting bracket takes over when the guess is off.
 //
 // Mapping: one lane per stream (every CDF evaluation depends on the stream's current state, so
-// unlike the encoder nothing can be hoisted to helper warps); a warp stages a
-// [32 streams][16 symbols] tile of (mean, scale) through shared memory with coalesced 64-byte
-// row segments, and the decoded symbols go back through the same tile so the x store is
-// coalesced too.
+// unlike the encoder nothing can be hoisted to helper warps); a warp stages
+// [32 streams][8 symbols] tiles of (mean, scale) through shared memory with cp.async, and the
+// decoded symbols go back through the same tile so the x store is coalesced too.  Neither the
+// parameter loads nor the bitstream words (prefetched one renormalisation ahead) put global
+// latency on the per-stream dependency chain.
 #include "flic_device.cuh"
 #include "flic_kernels.cuh"
 
 namespace flic {
 
-// Symbols per stream per tile.  16 keeps the tile at 4.3 KB per warp, so that registers (not
-// shared memory) limit residency: 32 warps per SM.
-constexpr int kDecTile = 16;
-constexpr int kRowsPerPass = kLanes / kDecTile;  // rows staged per warp-wide load
+// Symbols per stream per tile.  Tiles are double-buffered: while the lanes decode tile q the
+// parameters of tile q-1 arrive through cp.async (LDGSTS), so no global-load latency sits on the
+// serial decode chain.  8 symbols x 2 buffers is 4.6 KB per warp: registers, not shared memory,
+// limit residency.
+constexpr int kDecTile = 8;
+constexpr int kRowsPerPass = kLanes / kDecTile;  // tile rows one warp-wide copy covers
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -37,7 +48,7 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
                    int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
                    int32_t* __restrict__ status, int check_end) {
     __shared__ uint64_t s_tab[32];
-    __shared__ float2 s_tile[WARPS][kLanes][kDecTile + 1];
+    __shared__ float2 s_tile[WARPS][2][kLanes][kDecTile + 1];
     stage_exp_table(s_tab);
 
     const int lane = threadIdx.x & 31;
@@ -53,33 +64,55 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
     const int64_t wbeg = live ? word_offsets[stream] : 0;
     int64_t wpos = live ? word_offsets[stream + 1] : 0;  // one past the last unread word
     uint64_t state = live ? states[stream] : kRansL;
+    // the next word to pull is kept in a register, loaded one renormalisation ahead
+    uint32_t next_word = wpos > wbeg ? __ldg(packed + wpos - 1) : 0u;
     int32_t flags = 0;
-    float2(*tile)[kDecTile + 1] = s_tile[warp];
-    const int sub = lane / kDecTile;   // which of the rows of a pass this lane helps with
+    const int sub = lane / kDecTile;   // which row of a pass this lane copies
     const int col = lane % kDecTile;   // symbol within the tile row
 
-    const int64_t n_tiles = (max_len + kDecTile - 1) / kDecTile;
-    for (int64_t t = n_tiles - 1; t >= 0; --t) {
-        const int64_t t0 = t * kDecTile;
-        // ---- phase A: stage (mean, scale) of the tile; each half-warp loads one 64-byte row
-#pragma unroll 4
+    // stage (mean, scale) of tile q into buffer q & 1: every 8-lane group copies one 32-byte row
+    auto prefetch = [&](int64_t q) {
+        float2(*tile)[kDecTile + 1] = s_tile[warp][q & 1];
+        const int64_t i = q * kDecTile + col;
+#pragma unroll
         for (int p = 0; p < kLanes / kRowsPerPass; ++p) {
             const int r = p * kRowsPerPass + sub;
             const int64_t b_r = shfl_i64(beg, r);
             const int64_t l_r = shfl_i64(len, r);
-            const int64_t i = t0 + col;
-            if (i < l_r) tile[r][col] = make_float2(__ldg(mean + b_r + i), __ldg(scale + b_r + i));
+            if (i < l_r) {
+                cp_async_f32(&tile[r][col].x, mean + b_r + i);
+                cp_async_f32(&tile[r][col].y, scale + b_r + i);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int64_t n_tiles = (max_len + kDecTile - 1) / kDecTile;
+    if (n_tiles > 0) prefetch(n_tiles - 1);
+    for (int64_t q = n_tiles - 1; q >= 0; --q) {
+        if (q > 0) {
+            prefetch(q - 1);
+            cp_async_wait<1>();  // tile q has landed; tile q-1 may still be in flight
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
-        // ---- phase B: lane-per-stream, last symbol of the tile first
+        float2(*tile)[kDecTile + 1] = s_tile[warp][q & 1];
+        const int64_t t0 = q * kDecTile;
+        // ---- lane-per-stream, last symbol of the tile first
         const int64_t rem = len - t0;
         const int cnt = rem >= kDecTile ? kDecTile : (rem > 0 ? (int)rem : 0);
 #pragma unroll 1
         for (int j = kDecTile - 1; j >= 0; --j) {
             if (j < cnt) {
                 if (state < kRansL) {  // rans.pyx:87-89
-                    if (wpos > wbeg) state = (state << 32) | __ldg(packed + (--wpos));
-                    else flags |= ST_UNDERRUN;
+                    if (wpos > wbeg) {
+                        state = (state << 32) | next_word;
+                        --wpos;
+                        if (wpos > wbeg) next_word = __ldg(packed + wpos - 1);
+                    } else {
+                        flags |= ST_UNDERRUN;
+                    }
                 }
                 const float2 ms = tile[lane][j];
                 const int s = decode_symbol(state, ms.x, ms.y, s_tab, flags);
@@ -87,8 +120,8 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
             }
         }
         __syncwarp();
-        // ---- phase C: coalesced store of the decoded symbols
-#pragma unroll 4
+        // ---- coalesced store of the decoded symbols (32-byte row segments)
+#pragma unroll
         for (int p = 0; p < kLanes / kRowsPerPass; ++p) {
             const int r = p * kRowsPerPass + sub;
             const int64_t b_r = shfl_i64(beg, r);
@@ -96,7 +129,7 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
             const int64_t i = t0 + col;
             if (i < l_r) x_out[b_r + i] = tile[r][col].x;
         }
-        __syncwarp();
+        __syncwarp();  // buffer q & 1 is overwritten by the prefetch of tile q-2 next iteration
     }
     if (live) {
         if (check_end && (state != kRansL || wpos != wbeg)) flags |= ST_BAD_END_STATE;

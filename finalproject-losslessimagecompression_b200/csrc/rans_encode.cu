@@ -8,10 +8,10 @@
 //
 // Mapping.  A CTA owns 32 consecutive streams and walks them in tiles of 32 symbols per stream.
 // The work splits by what is parallel and what is not:
-//   producers (8 warps)  pass 1.  For each of the tile's 32 rows (one stream's 32 consecutive
+//   producers (4 or 8 warps)  pass 1.  For each of the tile's 32 rows (one stream's 32 consecutive
 //       symbols) a warp loads x, mean, scale as three coalesced 128-byte rows and evaluates
 //       (start, freq) -- the expensive FP64 part, perfectly parallel over symbols -- into a
-//       shared-memory tile.  Each producer warp does 4 rows per tile, loads issued up front.
+//       shared-memory tile.  Rows are taken 4 at a time, their loads issued up front.
 //   consumer (1 warp)    pass 2.  Lane l replays row l of the finished tile through the serial
 //       rANS recurrence, state in registers, and appends the emitted words to the stream's
 //       scratch region.
@@ -26,11 +26,16 @@
 
 namespace flic {
 
-constexpr int kEncProducers = 8;
-constexpr int kEncThreads = (kEncProducers + 1) * 32;
-constexpr int kRowsPerProducer = kLanes / kEncProducers;
+// Rows a producer warp loads (and then evaluates) back to back.
+constexpr int kRowBatch = 4;
 
-__global__ void __launch_bounds__(kEncThreads)
+// PRODUCERS per CTA.  The consumer issues ~1440 instructions per tile (32 steps x ~45) and a
+// producer 6400 / PRODUCERS; every resident warp gets the same share of its scheduler, so a CTA's
+// tile takes as long as its busiest warp.  4 producers balance the two roles (1600 vs 1440) and
+// keep the issue slots full when many CTAs are resident; 8 producers halve the latency of a
+// tile when only a few CTAs exist (few streams).
+template <int PRODUCERS>
+__global__ void __launch_bounds__((PRODUCERS + 1) * 32)
 rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                    int64_t n_streams, const uint64_t* __restrict__ init_states,
@@ -66,29 +71,32 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
         for (int64_t k = 0; k < n_tiles; ++k) {
             uint2(*tile)[kTile + 1] = s_tile[k & 1];
             const int64_t i = k * kTile + lane;
-            float xv[kRowsPerProducer], mv[kRowsPerProducer], sv[kRowsPerProducer];
-            bool on[kRowsPerProducer];
+#pragma unroll 1
+            for (int r0 = pw * kRowBatch; r0 < kLanes; r0 += PRODUCERS * kRowBatch) {
+                float xv[kRowBatch], mv[kRowBatch], sv[kRowBatch];
+                bool on[kRowBatch];
 #pragma unroll
-            for (int q = 0; q < kRowsPerProducer; ++q) {  // all loads of the warp's rows first
-                const int r = pw + q * kEncProducers;
-                on[q] = i < s_len[r];
-                xv[q] = mv[q] = 0.0f;
-                sv[q] = 1.0f;
-                if (on[q]) {
-                    const int64_t g = s_beg[r] + i;
-                    xv[q] = __ldg(x + g);
-                    mv[q] = __ldg(mean + g);
-                    sv[q] = __ldg(scale + g);
+                for (int q = 0; q < kRowBatch; ++q) {  // all loads of the batch first
+                    const int r = r0 + q;
+                    on[q] = i < s_len[r];
+                    xv[q] = mv[q] = 0.0f;
+                    sv[q] = 1.0f;
+                    if (on[q]) {
+                        const int64_t g = s_beg[r] + i;
+                        xv[q] = __ldg(x + g);
+                        mv[q] = __ldg(mean + g);
+                        sv[q] = __ldg(scale + g);
+                    }
                 }
-            }
 #pragma unroll
-            for (int q = 0; q < kRowsPerProducer; ++q) {
-                const int r = pw + q * kEncProducers;
-                if (on[q]) {
-                    int32_t f = 0;
-                    const SymbolTable e = make_table(xv[q], mv[q], sv[q], s_tab, f);
-                    tile[r][lane] = make_uint2(e.start, e.freq);
-                    if (f) atomicOr(&s_flags[r], f);  // rare
+                for (int q = 0; q < kRowBatch; ++q) {
+                    const int r = r0 + q;
+                    if (on[q]) {
+                        int32_t f = 0;
+                        const SymbolTable e = make_table(xv[q], mv[q], sv[q], s_tab, f);
+                        tile[r][lane] = make_uint2(e.start, e.freq);
+                        if (f) atomicOr(&s_flags[r], f);  // rare
+                    }
                 }
             }
             cta_sync();  // tile k complete; the consumer has finished tile k-1, so buffer (k+1)&1 is free
@@ -130,8 +138,12 @@ cudaError_t launch_rans_encode(const float* x, const float* mean, const float* s
                                uint64_t* states, int32_t* status, cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
     const int64_t blocks = (n_streams + kLanes - 1) / kLanes;
-    rans_encode_kernel<<<(unsigned)blocks, kEncThreads, 0, stream>>>(
-        x, mean, scale, offsets, n_streams, init_states, scratch, counts, states, status);
+    if (blocks >= (int64_t)sm_count() * 6)
+        rans_encode_kernel<4><<<(unsigned)blocks, 5 * 32, 0, stream>>>(
+            x, mean, scale, offsets, n_streams, init_states, scratch, counts, states, status);
+    else
+        rans_encode_kernel<8><<<(unsigned)blocks, 9 * 32, 0, stream>>>(
+            x, mean, scale, offsets, n_streams, init_states, scratch, counts, states, status);
     return cudaGetLastError();
 }
 

@@ -81,6 +81,24 @@ def test_uniform_partition_imagenet64_shape(oracle):
         assert torch.equal(xr, xd) and not status.any().item()
 
 
+def test_many_short_streams_exercise_the_large_grid_kernels(oracle):
+    """Above ~28 k streams the encoder switches to 4 producer warps per CTA and above ~76 k the
+    decoder to 4 warps per CTA; both variants must be bit-exact too (ragged, some empty streams)."""
+    from flic_b200 import rans
+    n, n_streams = 1_500_000, 90_000
+    x, mean, scale = gen("test", n, 77)
+    off = ragged_offsets(n, n_streams, 78)
+    words_o, woff_o, states_o, _ = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+    xd, md, sd = _cuda(x, mean, scale)
+    offd = torch.from_numpy(off).cuda()
+    enc = rans.encode_streams(xd, md, sd, offd)
+    assert np.array_equal(enc.word_offsets.cpu().numpy(), woff_o)
+    assert np.array_equal(_u64(enc.final_states), states_o)
+    assert np.array_equal(_u32(enc.words), words_o)
+    xr, end, status = rans.decode_streams(enc, md, sd, offd)
+    assert torch.equal(xr, xd) and not status.any().item() and bool((end == (1 << 32)).all().item())
+
+
 def test_empty_and_tiny_inputs():
     from flic_b200 import rans
     e = torch.empty(0, dtype=torch.float32, device="cuda")
