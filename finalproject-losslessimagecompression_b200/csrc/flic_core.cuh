@@ -139,6 +139,28 @@ FLIC_HD uint32_t f32_bits(float f) {
 #endif
 }
 
+// float -> int, truncating, saturating, NaN -> 0 (the device conversion's semantics)
+FLIC_HD int f2i_rz(float v) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rz(v);
+#else
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)v;
+#endif
+}
+FLIC_HD int d2i_rz(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2int_rz(v);
+#else
+    if (v != v) return 0;
+    if (v >= 2147483648.0) return 2147483647;
+    if (v <= -2147483648.0) return (-2147483647 - 1);
+    return (int)v;
+#endif
+}
+
 // ---- glibc expf ---------------------------------------------------------------------------------
 // T[i] = bits(2^(i/32)) - (i << 47).  Published table of glibc's __exp2f_data (N = 32).
 #define FLIC_EXP2F_TABLE                                                                          \
@@ -189,8 +211,10 @@ FLIC_HD float expf_glibc(float x, const uint64_t* tab) {  // x by value: clamped
 // ---- per-symbol model -----------------------------------------------------------------------------
 FLIC_HD int lower_of(float mean) {
     // (int) round((double)mean * 256.0 - 1024.0), C round(): half away from zero
+    // v is exact (24-bit significand times 2^8, minus 2^10); round half away from zero is
+    // trunc(v + copysign(0.5, v)), and that sum is exact too
     const double v = dsub(dmul((double)mean, 256.0), 1024.0);
-    return (int)round(v);
+    return d2i_rz(dadd(v, copysign(0.5, v)));
 }
 
 struct SymbolModel {
@@ -198,20 +222,30 @@ struct SymbolModel {
     double scale_d;  // (double)scale
     double rscale;   // RN(1 / scale_d)
     int lower;       // window origin in 1/256 units
-    int32_t flags;   // ST_ZERO_SCALE / ST_NONFINITE
 };
 
+// Parameters the arithmetic below is exact for: finite non-zero scale, and |mean| limited so that
+// every window index stays below 2^23 and the float arithmetic of rans.pyx:33 (x - lower) is
+// exact (8-bit image latents are within a few units of zero).  NaN fails every comparison.
+FLIC_HD bool params_ok(float mean, float scale) {
+    return (fabsf(mean) <= 16384.0f) && (fabsf(scale) < INFINITY) && (scale != 0.0f);
+}
+// Status bits for parameters that are not ok (slow path only).
+FLIC_HD int32_t param_flags(float mean, float scale) {
+    int32_t f = 0;
+    if (scale == 0.0f) f |= ST_ZERO_SCALE;
+    if (!(fabsf(mean) <= 16384.0f) || !(fabsf(scale) < INFINITY)) f |= ST_NONFINITE;
+    return f;
+}
+
+// The model is computed unconditionally; for parameters that are not ok its contents are
+// meaningless but harmless (no trap, no unbounded loop) and the stream is flagged by the caller.
 FLIC_HD SymbolModel make_model(float mean, float scale) {
     SymbolModel m;
-    m.flags = 0;
-    if (scale == 0.0f) m.flags |= ST_ZERO_SCALE;
-    // |mean| is limited so that every window index stays below 2^23 and the float arithmetic of
-    // rans.pyx:33 (x - lower) is exact; 8-bit image latents are within a few units of zero.
-    if (!(fabsf(mean) <= 16384.0f) || !(fabsf(scale) < INFINITY)) m.flags |= ST_NONFINITE;
     m.mean_d = (double)mean;
     m.scale_d = (double)scale;
     m.rscale = drcp(m.scale_d);
-    m.lower = (m.flags & ST_NONFINITE) ? 0 : lower_of(mean);
+    m.lower = lower_of(mean);
     return m;
 }
 
@@ -254,32 +288,26 @@ FLIC_HD void cdf_pair(int s, const SymbolModel& m, const uint64_t* tab, int& c_l
     c_lo = part1_at(a_lo, m, tab) + (s - m.lower);
 }
 
-// Symbol value -> integer grid index; ok=false when x is not an exact multiple of 1/256 that the
-// window arithmetic represents exactly (then the reference's own result is garbage, App. D).
-FLIC_HD int symbol_index(float x, bool& ok) {
-    const float xs = x * 256.0f;
-    ok = fabsf(xs) < 8388608.0f;
-    const int s = ok ? (int)xs : 0;
-    ok = ok && ((float)s == xs);
-    return s;
-}
-
 struct SymbolTable {
     uint32_t start;  // CDF(x - 1/256)
     uint32_t freq;   // CDF(x) - start  (>= 1)
 };
 
 // encode pass 1 for one symbol (rans.pyx:50-56).  flags accumulates status bits.
+// A symbol is codable when its parameters are ok, x is an exact multiple of 1/256 and its grid
+// index lies in [lower, lower + 2047]; then every float operation of rans.pyx:33 is exact and
+// part2 is plain integer arithmetic.  Anything else makes the reference silently emit an
+// undecodable stream; here the stream is flagged and a harmless entry keeps
+// the coder alive.
 FLIC_HD SymbolTable make_table(float x, float mean, float scale, const uint64_t* tab, int32_t& flags) {
     const SymbolModel m = make_model(mean, scale);
-    bool ok;
-    const int s = symbol_index(x, ok);
-    int32_t f = m.flags;
-    if (!ok || s < m.lower || s > m.lower + (kWindow - 1)) f |= ST_OUT_OF_WINDOW;
+    const float xs = x * 256.0f;
+    const int s = f2i_rz(xs);
+    const bool in_window = ((float)s == xs) && ((uint32_t)(s - m.lower) < (uint32_t)kWindow);
     SymbolTable t;
-    if (f) {  // keep the coder alive with a harmless entry; the stream is reported as failed
+    if (!(in_window && params_ok(mean, scale))) {
+        flags |= param_flags(mean, scale) | (in_window ? 0 : ST_OUT_OF_WINDOW);
         t.start = 0; t.freq = 1;
-        flags |= f;
         return t;
     }
     int c0, c1;
@@ -296,7 +324,8 @@ FLIC_HD SymbolTable make_table(float x, float mean, float scale, const uint64_t*
 // makes it exact.
 FLIC_HD bool rans_push(uint64_t& state, uint32_t start, uint32_t freq, uint32_t& word) {
     bool emit = false;
-    if (state >= ((uint64_t)freq << 40)) {
+    // state >= freq << 40: the threshold's low 32 bits are zero, so only the high words compare
+    if ((uint32_t)(state >> 32) >= (freq << 8)) {
         word = (uint32_t)state;
         state >>= 32;
         emit = true;
@@ -425,7 +454,7 @@ FLIC_HD int decode_symbol(uint64_t& state, float mean, float scale,
                                              const uint64_t* s_tab, int32_t& flags) {
     const uint32_t mod = (uint32_t)state & kProbMask;
     const SymbolModel m = make_model(mean, scale);
-    flags |= m.flags;
+    if (!params_ok(mean, scale)) flags |= param_flags(mean, scale);
     const int g = guess_symbol(mod, mean, scale, m.lower);
     int c_lo, c_hi;
     cdf_pair(g, m, s_tab, c_lo, c_hi);

@@ -74,7 +74,7 @@ int hh_decode(const uint32_t* words, int64_t n_words, uint64_t state, const floa
         }
         const uint32_t mod = (uint32_t)state & kProbMask;
         SymbolModel m = make_model(mean[i], scale[i]);
-        flags |= m.flags;
+        flags |= param_flags(mean[i], scale[i]);
         SearchState st = search_begin(mod, mean[i], scale[i], m);
         while (!st.done) {
             const int c = cdf_at(st.probe, m, kTab);
