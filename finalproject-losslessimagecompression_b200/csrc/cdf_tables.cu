@@ -19,10 +19,19 @@ cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
     stage_exp_table(s_tab);
     int32_t flags = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const SymbolTable t = make_table(__ldg(x + i), __ldg(mean + i), __ldg(scale + i), s_tab, flags);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // software pipeline: the next symbol's parameters are in flight while this one is evaluated,
+    // so HBM latency never sits in front of the arithmetic
+    float xv = __ldg(x + i), mv = __ldg(mean + i), sv = __ldg(scale + i);
+    for (; i < n; i += stride) {
+        const int64_t nx = i + stride;
+        float xn = 0.0f, mn = 0.0f, sn = 1.0f;
+        if (nx < n) { xn = __ldg(x + nx); mn = __ldg(mean + nx); sn = __ldg(scale + nx); }
+        const SymbolTable t = make_table(xv, mv, sv, s_tab, flags);
         start[i] = t.start;
         freq[i] = t.freq;
+        xv = xn; mv = mn; sv = sn;
     }
     if (flags) atomicOr(status_word, flags);
 }

@@ -161,6 +161,60 @@ FLIC_HD int d2i_rz(double v) {
 #endif
 }
 
+// ---- conversions done on the FP64 / integer pipes -------------------------------------------------
+// The conversion instructions (F2F, F2I, I2F) issue to the quarter-rate XU pipe on sm_100 -- one
+// costs as much pipe time as four FP64 operations -- and the coder needs about twenty of them
+// per symbol when written naively.  The helpers below get the same values from exact FP64
+// additions with "magic" constants and from integer operations on the bit patterns.  They are
+// portable C++ (the host harness runs the same text), except the truncating add.
+
+// v rounded to a 24-bit significand, ties to even: (double)(float)v for every v whose float image
+// is normal.  M = 1.5 * 2^(e+29), e = exponent of v, puts the sum in the binade whose ulp is a
+// float's ulp in v's binade (2^(e-23)); the FP64 adder does the rounding and the subtraction is
+// exact.  M's significand is even in those ulps, so ties break exactly as the conversion's do.
+// Differences from the conversion pair: no overflow to inf and no subnormal range.  Callers show
+// that both only occur where part1 is saturated anyway (see part1_at).
+FLIC_HD double round24(double v) {
+    const uint64_t b = f64_bits(v);
+    const double M = bits_f64((b & 0x7ff0000000000000ull) + 0x01d8000000000000ull);
+    return dsub(dadd(v, M), M);
+}
+
+// floor(w) for 0 <= w < 2^32 as an integer: w + 2^52 rounded toward zero leaves floor(w) in the
+// low word of the sum.
+FLIC_HD uint32_t floor_nonneg_u32(double w) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(__dadd_rz(w, 4503599627370496.0));
+#else
+    return (uint32_t)(uint64_t)floor(w);
+#endif
+}
+
+// (double)n for |n| < 2^31, exact: the bits of 2^52 + 2^51 + n are 0x4338000000000000 + n.
+FLIC_HD double i32_to_f64(int n) {
+    return dsub(bits_f64(0x4338000000000000ull + (uint64_t)(int64_t)n), 6755399441055744.0);
+}
+// (double)n for n < 2^32, exact.
+FLIC_HD double u32_to_f64(uint32_t n) {
+    return dsub(bits_f64(0x4330000000000000ull | (uint64_t)n), 4503599627370496.0);
+}
+// (double)(hi * 2^32 + lo), correctly rounded (one rounding, in the last add):
+// bits 0x45300000:hi = 2^84 + hi 2^32, bits 0x43300000:lo = 2^52 + lo.
+FLIC_HD double u64_to_f64(uint32_t hi, uint32_t lo) {
+    const double dh = dsub(bits_f64(0x4530000000000000ull | (uint64_t)hi), 19342813118337666422669312.0);  // 2^84 + 2^52
+    return dadd(dh, bits_f64(0x4330000000000000ull | (uint64_t)lo));
+}
+
+// q with its magnitude limited to [0, 128 (1 + 2^-20)): beyond |q| = 128 the caller's result is
+// saturated and only the sign matters.  Integer min on the high word; NaN becomes finite too.
+FLIC_HD double clamp_mag128(double q) {
+    const uint64_t b = f64_bits(q);
+    const uint32_t hi = (uint32_t)(b >> 32);
+    uint32_t ah = hi & 0x7fffffffu;
+    ah = ah < 0x40600000u ? ah : 0x40600000u;
+    return bits_f64(((uint64_t)(ah | (hi & 0x80000000u)) << 32) | (uint32_t)b);
+}
+
 // ---- glibc expf ---------------------------------------------------------------------------------
 // T[i] = bits(2^(i/32)) - (i << 47).  Published table of glibc's __exp2f_data (N = 32).
 #define FLIC_EXP2F_TABLE                                                                          \
@@ -175,25 +229,21 @@ FLIC_HD int d2i_rz(double v) {
 
 // `tab` points at the 32-entry table: shared memory on the device (each lane indexes its own
 // entry, so constant memory would serialise), a static array on the host.
-// Branch-free; equal to glibc's expf for every non-NaN float (tests sweep all of them).
+//
+// exp_core(xd) is the double-precision body of glibc's expf for xd = (double)x: it returns the
+// product y * s whose conversion to float is the function's result.  Valid (no exponent
+// overflow in s) for |xd| < 700.
 // The polynomial is evaluated with fused multiply-adds.  oracle/rans_oracle.c proves (exhaustive
 // sweep over |x| <= 104, tests/test_oracle_pinning.py) that fused and unfused evaluation both
 // agree with the host libm everywhere except two inputs deep inside part1's saturated range.
-FLIC_HD float expf_glibc(float x, const uint64_t* tab) {  // x by value: clamped below
+// `neg` evaluates exp(-xd): (-InvLn2N) * xd is bit-identical to InvLn2N * (-xd).
+FLIC_HD double exp_core(double xd, const uint64_t* tab, bool neg) {
     const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
     const double Shift = 0x1.8p+52;
     const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0;
     const double C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0;
     const double C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
-    // glibc special-cases |x| >= 88: x > 0x1.62e42ep6 -> +inf, x < -0x1.9fe368p6 -> 0, inf/nan
-    // passthrough.  Clamping x to [-104, 89] and running the main path gives the same floats:
-    // e^89 overflows the final double->float conversion to +inf, e^-104 rounds to 0 (it is below
-    // half the smallest subnormal, the very definition of glibc's underflow threshold), and the
-    // results in between are the main path's anyway.  NaN cannot reach here from a valid stream
-    // (status NONFINITE / ZERO_SCALE); it is mapped to the lower clamp.
-    x = fminf(fmaxf(x, -104.0f), 89.0f);
-    const double xd = (double)x;
-    const double z = dmul(InvLn2N, xd);
+    const double z = dmul(neg ? -InvLn2N : InvLn2N, xd);
     double kd = dadd(z, Shift);
     const uint64_t ki = f64_bits(kd);
     kd = dsub(kd, Shift);
@@ -204,18 +254,31 @@ FLIC_HD float expf_glibc(float x, const uint64_t* tab) {  // x by value: clamped
     const double r2 = dmul(r, r);
     double y = dfma(C2, r, 1.0);
     y = dfma(zz, r2, y);
-    y = dmul(y, s);
-    return d2f(y);
+    return dmul(y, s);
+}
+
+// glibc's expf, branch-free; equal to it for every non-NaN float (tests sweep all of them).
+// glibc special-cases |x| >= 88: x > 0x1.62e42ep6 -> +inf, x < -0x1.9fe368p6 -> 0, inf/nan
+// passthrough.  Clamping x to [-104, 89] and running the main path gives the same floats:
+// e^89 overflows the final double->float conversion to +inf, e^-104 rounds to 0 (it is below
+// half the smallest subnormal, the very definition of glibc's underflow threshold), and the
+// results in between are the main path's anyway.  NaN is mapped to the lower clamp.
+// The coder itself uses exp_core() directly (part1_at); this wrapper exists for the sweeps.
+FLIC_HD float expf_glibc(float x, const uint64_t* tab) {  // x by value: clamped below
+    x = fminf(fmaxf(x, -104.0f), 89.0f);
+    return d2f(exp_core((double)x, tab, false));
 }
 
 // ---- per-symbol model -----------------------------------------------------------------------------
-FLIC_HD int lower_of(float mean) {
-    // (int) round((double)mean * 256.0 - 1024.0), C round(): half away from zero
-    // v is exact (24-bit significand times 2^8, minus 2^10); round half away from zero is
-    // trunc(v + copysign(0.5, v)), and that sum is exact too
-    const double v = dsub(dmul((double)mean, 256.0), 1024.0);
-    return d2i_rz(dadd(v, copysign(0.5, v)));
+FLIC_HD int lower_of_d(double mean_d) {
+    // (int) round(mean_d * 256.0 - 1024.0), C round(): half away from zero.
+    // v is exact (24-bit significand times 2^8, minus 2^10), so one fma computes it; |v| + 0.5
+    // is exact too, and half away from zero is sign(v) * floor(|v| + 0.5).
+    const double v = dfma(mean_d, 256.0, -1024.0);
+    const int n = (int)floor_nonneg_u32(dadd(fabs(v), 0.5));
+    return (int64_t)f64_bits(v) < 0 ? -n : n;
 }
+FLIC_HD int lower_of(float mean) { return lower_of_d((double)mean); }
 
 struct SymbolModel {
     double mean_d;   // (double)mean
@@ -245,7 +308,7 @@ FLIC_HD SymbolModel make_model(float mean, float scale) {
     m.mean_d = (double)mean;
     m.scale_d = (double)scale;
     m.rscale = drcp(m.scale_d);
-    m.lower = lower_of(mean);
+    m.lower = lower_of_d(m.mean_d);
     return m;
 }
 
@@ -262,27 +325,70 @@ FLIC_HD double div_by_scale(double a, const SymbolModel& m) {
 
 // part1 of CDF at the point whose (xq + 1/512) is `a`:
 //   (int) roundf( (float)( 1/(1+expf(-arg)) * 16775168 ) ),  arg = (float)( (a - mean) / scale ).
+// The three float roundings are round24() on doubles, never leaving the FP64 pipe.  Where that
+// differs from a real conversion the result is the same:
+//   * arg: |q| >= 2^128 would convert to inf and glibc's expf special-cases |x| >= 88; here q is
+//     limited to |q| < 128.001 first.  For arg in (88.7, 128] the reference has e = inf, p = 0,
+//     part1 = 0, and here e <= e^128.001 is a finite double, p < 2^-184, part1 = 0; for arg in
+//     [-128, -103.9) the reference has e = 0 and here e < 2^-149, 1 + e == 1 both ways.
+//     |q| < 2^-126 (float subnormal) keeps more bits here, but expf(-arg) == 1.0f for all
+//     |arg| < 2^-25.
+//   * e: a float-subnormal e (< 2^-126) keeps more bits here, but 1 + e == 1 below 2^-53.
+//   * the product is at most 16775168 and at least 2^-184 * A > 0: no range issue; below 2^-126
+//     both round to 0.
+// Which of the three float roundings use the conversion instructions (XU pipe) and which the
+// FP64-pipe round24().  All eight combinations give identical tables (tools/variant_bench.cu);
+// measured on B200, K1 runs 142 / 149 / 155 / 156 G symbols/s for 000 / 001 / 101 / 111: the
+// XU pipe (8 cycles per warp-instruction) and the FP64 pipe (2 cycles) overlap, so the work is
+// split between them.
+#ifndef FLIC_ARG_XU
+#define FLIC_ARG_XU 1
+#endif
+#ifndef FLIC_E_XU
+#define FLIC_E_XU 0
+#endif
+#ifndef FLIC_V_XU
+#define FLIC_V_XU 1
+#endif
 FLIC_HD int part1_at(double a, const SymbolModel& m, const uint64_t* tab) {
     const double t4 = dsub(a, m.mean_d);
-    const float arg = d2f(div_by_scale(t4, m));
-    // e = +inf (arg <= -88.7) would poison the reciprocal; FLT_MAX gives the same part1 = 0
-    const float e = fminf(expf_glibc(-arg, tab), 3.402823466e+38f);
-    const double p = drcp(dadd(1.0, (double)e));
+#if FLIC_ARG_XU
+    const double arg = (double)fminf(fmaxf(d2f(div_by_scale(t4, m)), -128.0f), 128.0f);
+#else
+    const double arg = round24(clamp_mag128(div_by_scale(t4, m)));
+#endif
+#if FLIC_E_XU
+    const double e = (double)fminf(d2f(exp_core(arg, tab, true)), 3.402823466e+38f);
+#else
+    const double e = round24(exp_core(arg, tab, true));
+#endif
+    const double p = drcp(dadd(1.0, e));
+#if FLIC_V_XU
     return round_half_away_nonneg(d2f(dmul(p, kPart1Scale)));
+#else
+    const double v = round24(dmul(p, kPart1Scale));
+    return (int)floor_nonneg_u32(dadd(v, 0.5));  // roundf of a non-negative float: floor(v + 0.5), exact sum
+#endif
+}
+
+// (double)xq + 1/512 = (2 s + 1) / 512 exactly, built without a conversion: the bits of
+// 1.5 * 2^43 + n / 512 are 0x42a8000000000000 + n (ulp 2^-9 in that binade).
+FLIC_HD double half_bin_point(int s) {
+    const int n = 2 * s + 1;
+    return dsub(bits_f64(0x42a8000000000000ull + (uint64_t)(int64_t)n), 13194139533312.0);
 }
 
 // CDF(s/256) for integer symbol s: part1 + part2, part2 = round((xq - lower_f) * 256) + 1
 // = s - lower + 1 exactly when |s| and |lower| are below 2^24 (both floats exact, difference
-// exact).  (double)xq + 1/512 = (2 s + 1) / 512 exactly.
+// exact).
 FLIC_HD int cdf_at(int s, const SymbolModel& m, const uint64_t* tab) {
-    const double a = dmul((double)(2 * s + 1), 0.001953125);
-    return part1_at(a, m, tab) + (s - m.lower + 1);
+    return part1_at(half_bin_point(s), m, tab) + (s - m.lower + 1);
 }
 
 // CDF(s-1) and CDF(s) together: the (start, end) pair of symbol s (rans.pyx:52-53, :106-107).
 // The two evaluations are independent and interleave in the instruction stream.
 FLIC_HD void cdf_pair(int s, const SymbolModel& m, const uint64_t* tab, int& c_lo, int& c_hi) {
-    const double a_hi = dmul((double)(2 * s + 1), 0.001953125);
+    const double a_hi = half_bin_point(s);
     const double a_lo = dsub(a_hi, 0.00390625);  // exact
     c_hi = part1_at(a_hi, m, tab) + (s - m.lower + 1);
     c_lo = part1_at(a_lo, m, tab) + (s - m.lower);
@@ -318,24 +424,46 @@ FLIC_HD SymbolTable make_table(float x, float mean, float scale, const uint64_t*
 }
 
 // ---- rANS state machine ---------------------------------------------------------------------------
+// 1/a biased low: (1/a)(1 - 2^-49) to within 2^-52 relative (hardware seed with relative error
+// e0 ~ 2^-20, one cubic Newton step whose residual carries the bias; the neglected terms are
+// e0^3 and 2^-49 e0).  Feeds the quotient estimate below, which is corrected in integers.
+FLIC_HD double rcp_biased_low(double a) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = __fma_rn(-a, y, 0x1.ffffffffffff8p-1);  // (1 - 2^-49) - a y
+    e = __fma_rn(e, e, e);
+    return __fma_rn(y, e, y);
+#else
+    return (1.0 / a) * 0x1.ffffffffffff8p-1;
+#endif
+}
+
 // Encoder step (rans.pyx:62-65).  Returns true and sets `word` when a 32-bit word is emitted.
-// The 64-by-24-bit division uses a double reciprocal: after renormalisation
-// state < freq << 40, so q < 2^40 and the estimate is off by at most one; the integer fix-up
-// makes it exact.
+// state / freq (64 by 24 bits) through FP64: after renormalisation state < freq << 40, so
+// q < 2^40.  qd = state_d * rf with rf biased low by 2^-49 is never above the real quotient and
+// less than 2^-8 below it (relative errors: bias 2^-49, state_d 2^-53, rf 2^-52, product 2^-53;
+// times q < 2^40), so floor(qd) is q or q - 1 and one integer correction makes it exact.
+// The remainder fits 32 bits, so it is computed modulo 2^32.
 FLIC_HD bool rans_push(uint64_t& state, uint32_t start, uint32_t freq, uint32_t& word) {
-    bool emit = false;
+    uint32_t hi = (uint32_t)(state >> 32), lo = (uint32_t)state;
     // state >= freq << 40: the threshold's low 32 bits are zero, so only the high words compare
-    if ((uint32_t)(state >> 32) >= (freq << 8)) {
-        word = (uint32_t)state;
-        state >>= 32;
-        emit = true;
-    }
-    const double rf = drcp((double)freq);
-    uint64_t q = (uint64_t)dmul((double)state, rf);
-    int64_t rem = (int64_t)(state - q * (uint64_t)freq);
-    if (rem < 0) { q -= 1; rem += freq; }
-    else if (rem >= (int64_t)freq) { q += 1; rem -= freq; }
-    state = (q << 24) + (uint64_t)rem + start;
+    const bool emit = hi >= (freq << 8);
+    if (emit) { word = lo; lo = hi; hi = 0; }
+    const double rf = rcp_biased_low(u32_to_f64(freq));
+    const double qd = dmul(u64_to_f64(hi, lo), rf);
+#if defined(__CUDA_ARCH__)
+    const uint64_t qb = (uint64_t)__double_as_longlong(__dadd_rz(qd, 4503599627370496.0));  // 2^52 + floor(qd)
+#else
+    const uint64_t qb = (uint64_t)floor(qd);
+#endif
+    const uint32_t q_lo = (uint32_t)qb;
+    uint32_t rem = lo - q_lo * freq;              // state - q freq, in [0, 2 freq)
+    const bool up = rem >= freq;                  // q was one short
+    // new state = ((q + up) << 24) + (rem - up freq) + start; the exponent bits of qb leave through
+    // the top of the shift (q < 2^40)
+    const uint64_t add = (uint64_t)(rem + start) + (up ? (uint64_t)(0x1000000u - freq) : 0ull);
+    state = (qb << 24) + add;
     return emit;
 }
 
@@ -347,47 +475,41 @@ FLIC_HD void rans_pop(uint64_t& state, uint32_t start, uint32_t freq) {
 // ---- decoder symbol search ----------------------------------------------------------------------
 // First guess for "smallest s with CDF(s) > mod" from the continuous model
 //   g(s) = A sigmoid((s + 0.5 - 256 mean) / (256 scale)) + (s - lower + 1),  A = 16775168
-// solved for g = mod + 0.5 with a logit start and one Newton step in float.  Only speed depends on it.
+// solved for g = mod + 0.5: start at u0 = logit(p0), p0 = (mod - 1024) / A (the sigmoid term alone,
+// window centre), then one Newton step on h(u) = A sig(u) + c u + (m - lower - mod),
+// u = (s + 0.5 - m) / c, m = 256 mean, c = 256 scale.  At u0 the sigmoid is p0 by construction, so
+// the step needs no exponential: A sig(u0) = P and A (1 - sig(u0)) = Q with the integers
+// P = mod - 1024 and Q = A - P, each kept >= 2 in the tails (h then uses the clamped value).
+// Three MUFU operations (two lg2, one rcp).  Only speed depends on the guess.
 FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
-    const float A = 16775168.0f;
     const float m = mean * 256.0f;
     const float c = scale * 256.0f;
-    // h(u) = A sig(u) + c u + (m - lower - mod), u = (s + 0.5 - m) / c.  In the upper half the
-    // constant A is folded into the integer (mod - A) and A sig(u) is written A - A (1 - sig(u)),
-    // so that every float term stays small and the residual keeps sub-bin precision in the tails.
     const int mi = (int)mod;
-    const bool upper = mi > 8388608;
-    const float K = (m - (float)lower) - (float)(upper ? mi - 16775168 : mi);
-    float p0 = ((float)mi - 1024.0f) * (1.0f / A);
-    p0 = fminf(fmaxf(p0, 1e-7f), 1.0f - 1e-7f);
+    int P = mi - 1024, Q = 16776192 - mi;
+    P = P < 2 ? 2 : P;
+    Q = Q < 2 ? 2 : Q;
+    // A sig(u0) - mod: -1024 unless a tail clamp moved P or Q (exact in integers)
+    const int off = P - Q + 16776192 - 2 * mi;
+    const float Pf = (float)P, Qf = (float)Q;
 #if defined(__CUDA_ARCH__)
-    float u = __logf(__fdividef(p0, 1.0f - p0));
+    const float u0 = (__log2f(Pf) - __log2f(Qf)) * 0.693147181f;
 #else
-    float u = logf(p0 / (1.0f - p0));
+    const float u0 = (log2f(Pf) - log2f(Qf)) * 0.693147181f;
 #endif
-    {   // one Newton step: >= 99.98 % of guesses are then exact on every tested distribution;
-        // a miss only costs extra evaluations in the bracket search
+    const float h = ffma(c, u0, (m - (float)lower) + (float)off);
+    const float dh = ffma(Pf * (1.0f / 16775168.0f), Qf, c);
 #if defined(__CUDA_ARCH__)
-        const float t = __expf(-fabsf(u));
-        const float r = __fdividef(1.0f, 1.0f + t);
+    const float u1 = u0 - __fdividef(h, dh);
+    // ceil through a round-up add of 1.5 * 2^23 (exact integer in the low mantissa bits when
+    // |sr| < 2^22; anything else is clamped into the window below)
+    const float sr = ffma(c, u1, m - 0.5f);
+    int g = (int)(__float_as_uint(__fadd_ru(sr, 12582912.0f)) - 0x4b400000u);
 #else
-        const float t = expf(-fabsf(u));
-        const float r = 1.0f / (1.0f + t);
-#endif
-        const float big = r, small = t * r;          // sig(|u|), 1 - sig(|u|)
-        const float sg = u >= 0.0f ? big : small;    // sig(u)
-        const float cs = u >= 0.0f ? small : big;    // 1 - sig(u)
-        const float h = ffma(c, u, ffma(upper ? -A : A, upper ? cs : sg, K));
-        const float dh = ffma(A * big, small, c);
-#if defined(__CUDA_ARCH__)
-        u -= __fdividef(h, dh);
-#else
-        u -= h / dh;
-#endif
-    }
-    const float sr = ceilf(ffma(c, u, m - 0.5f));
+    const float u1 = ffma(-h, 1.0f / dh, u0);
+    const float sr = ceilf(ffma(c, u1, m - 0.5f));
     int g = lower + 1024;
-    if (fabsf(sr) < 1.0e9f) g = (int)sr;
+    if (fabsf(sr) < 4.0e6f) g = (int)sr;
+#endif
     g = g < lower ? lower : g;
     g = g > lower + (kWindow - 1) ? lower + (kWindow - 1) : g;
     return g;
