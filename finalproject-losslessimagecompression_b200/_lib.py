@@ -18,6 +18,7 @@ ST_UNDERRUN = 4
 ST_NONFINITE = 8
 ST_BAD_END_STATE = 16
 ST_NO_SYMBOL = 32
+ST_TOO_LONG = 64
 
 E_ARG, E_CAPACITY, E_NOMEM, E_STATUS = -1, -2, -3, -4
 
@@ -92,7 +93,8 @@ def kernel_launches() -> int:
 def status_message(bits: int) -> str:
     names = [(ST_ZERO_SCALE, "scale == 0"), (ST_OUT_OF_WINDOW, "symbol outside the 2048-bin window / off the 1/256 grid"),
              (ST_UNDERRUN, "word buffer under-run / output too small"), (ST_NONFINITE, "non-finite scale or |mean| > 16384"),
-             (ST_BAD_END_STATE, "decoder did not end at 1<<32"), (ST_NO_SYMBOL, "no symbol matches (corrupt stream)")]
+             (ST_BAD_END_STATE, "decoder did not end at 1<<32"), (ST_NO_SYMBOL, "no symbol matches (corrupt stream)"),
+             (ST_TOO_LONG, "a single stream of 2^32 words or more")]
     return "; ".join(n for b, n in names if bits & b) or "ok"
 
 

@@ -39,6 +39,7 @@ enum : int32_t {
     ST_NONFINITE = 8,      // NaN/inf scale, or |mean| > 16384 (window arithmetic no longer exact)
     ST_BAD_END_STATE = 16, // decoder did not return to 1<<32 (rans/test.py:26 prints it)
     ST_NO_SYMBOL = 32,     // decoder: mod >= CDF(upper); reference would emit lower+2048
+    ST_TOO_LONG = 64,      // decoder: a single stream of 2^32 words or more is not supported
 };
 
 constexpr uint64_t kRansL = 0x100000000ull;  // rans.pyx:13
@@ -492,14 +493,19 @@ FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
     const int off = P - Q + 16776192 - 2 * mi;
     const float Pf = (float)P, Qf = (float)Q;
 #if defined(__CUDA_ARCH__)
-    const float u0 = (__log2f(Pf) - __log2f(Qf)) * 0.693147181f;
+    float lp, lq;   // P, Q >= 2 are normal floats: the flush-to-zero forms skip the subnormal fix-ups
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(Pf));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lq) : "f"(Qf));
+    const float u0 = (lp - lq) * 0.693147181f;
 #else
     const float u0 = (log2f(Pf) - log2f(Qf)) * 0.693147181f;
 #endif
     const float h = ffma(c, u0, (m - (float)lower) + (float)off);
     const float dh = ffma(Pf * (1.0f / 16775168.0f), Qf, c);
 #if defined(__CUDA_ARCH__)
-    const float u1 = u0 - __fdividef(h, dh);
+    float rdh;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdh) : "f"(dh));
+    const float u1 = ffma(-h, rdh, u0);
     // ceil through a round-up add of 1.5 * 2^23 (exact integer in the low mantissa bits when
     // |sr| < 2^22; anything else is clamped into the window below)
     const float sr = ffma(c, u1, m - 0.5f);

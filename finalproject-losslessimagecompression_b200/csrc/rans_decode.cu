@@ -59,14 +59,19 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
     const bool live = stream < n_streams;
 
     const int64_t beg = live ? offsets[stream] : 0;
-    const int64_t len = live ? offsets[stream + 1] - beg : 0;
-    const int64_t max_len = warp_max_i64(len);
+    int64_t len = live ? offsets[stream + 1] - beg : 0;
     const int64_t wbeg = live ? word_offsets[stream] : 0;
-    int64_t wpos = live ? word_offsets[stream + 1] : 0;  // one past the last unread word
+    const int64_t wcount = live ? word_offsets[stream + 1] - wbeg : 0;
+    const bool too_long = wcount > 0xffffffffll;
+    if (too_long) len = 0;
+    const int64_t max_len = warp_max_i64(len);
+    // words are consumed from the last emitted to the first: wrem counts the unread ones, and the
+    // next word to pull is kept in a register, loaded one renormalisation ahead
+    const uint32_t* wp = packed + wbeg;
+    uint32_t wrem = too_long ? 0u : (uint32_t)wcount;
     uint64_t state = live ? states[stream] : kRansL;
-    // the next word to pull is kept in a register, loaded one renormalisation ahead
-    uint32_t next_word = wpos > wbeg ? __ldg(packed + wpos - 1) : 0u;
-    int32_t flags = 0;
+    uint32_t next_word = wrem ? __ldg(wp + (wrem - 1)) : 0u;
+    int32_t flags = too_long ? ST_TOO_LONG : 0;
     const int sub = lane / kDecTile;   // which row of a pass this lane copies
     const int col = lane % kDecTile;   // symbol within the tile row
 
@@ -106,10 +111,10 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
         for (int j = kDecTile - 1; j >= 0; --j) {
             if (j < cnt) {
                 if (state < kRansL) {  // rans.pyx:87-89
-                    if (wpos > wbeg) {
+                    if (wrem) {
                         state = (state << 32) | next_word;
-                        --wpos;
-                        if (wpos > wbeg) next_word = __ldg(packed + wpos - 1);
+                        --wrem;
+                        if (wrem) next_word = __ldg(wp + (wrem - 1));
                     } else {
                         flags |= ST_UNDERRUN;
                     }
@@ -132,7 +137,7 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
         __syncwarp();  // buffer q & 1 is overwritten by the prefetch of tile q-2 next iteration
     }
     if (live) {
-        if (check_end && (state != kRansL || wpos != wbeg)) flags |= ST_BAD_END_STATE;
+        if (check_end && !too_long && (state != kRansL || wrem != 0)) flags |= ST_BAD_END_STATE;
         end_states[stream] = state;
         status[stream] = flags;
     }

@@ -113,7 +113,7 @@ class EncodedStreams:
         bits = int(torch.bitwise_or(self.status, 0).max().item()) if self.status.numel() else 0
         if bits:
             allbits = 0
-            for b in (1, 2, 4, 8, 16, 32):
+            for b in (1, 2, 4, 8, 16, 32, 64):
                 if bool((self.status & b).any().item()):
                     allbits |= b
             _lib.raise_for_status(allbits)
@@ -214,7 +214,7 @@ def check_status(status: torch.Tensor) -> None:
         return
     if bool((status != 0).any().item()):
         allbits = 0
-        for b in (1, 2, 4, 8, 16, 32):
+        for b in (1, 2, 4, 8, 16, 32, 64):
             if bool((status & b).any().item()):
                 allbits |= b
         _lib.raise_for_status(allbits)

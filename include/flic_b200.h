@@ -48,6 +48,7 @@ extern "C" {
 #define FLIC_ST_NONFINITE 8     /* NaN/inf scale or |mean| > 16384 */
 #define FLIC_ST_BAD_END_STATE 16 /* decoder did not end at 1<<32 with all words consumed (rans/test.py:26) */
 #define FLIC_ST_NO_SYMBOL 32    /* decoder: no symbol in the window matches (corrupt input) */
+#define FLIC_ST_TOO_LONG 64     /* decoder: one stream holds 2^32 words or more (not supported) */
 
 typedef void* flic_cuda_stream_t; /* a cudaStream_t */
 
