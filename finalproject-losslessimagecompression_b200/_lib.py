@@ -33,6 +33,7 @@ SIGNATURES = {
     "flic_kernel_launches": (_i64, []),
     "flic_cdf_tables": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_debug_expf": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "flic_debug_part1": (C.c_int, [_vp, _vp, _i64, _vp]),
     "flic_encode_workspace_bytes": (_i64, [_i64, _i64]),
     "flic_rans_encode": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_rans_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp]),

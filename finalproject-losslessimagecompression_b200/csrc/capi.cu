@@ -1,8 +1,9 @@
 // capi.cu -- the C ABI declared in include/flic_b200.h.
 //
 // Thin: argument checks, workspace carving, launches.  The host entry points add the
-// host<->device copies (chunked and double-buffered over two CUDA streams so that the PCIe
-// transfer of one chunk overlaps the kernels of the previous one) and one synchronisation.
+// host<->device copies, chunked over three CUDA streams so that the upload of one chunk, the
+// kernels of the previous one and the download of the one before overlap, and synchronise once
+// before returning.
 #include "../../include/flic_b200.h"
 #include "flic_core.cuh"
 #include "flic_kernels.cuh"
@@ -84,6 +85,13 @@ int flic_cdf_tables(const float* x, const float* mean, const float* scale, int64
 int flic_debug_expf(const float* x, float* y, int64_t n, flic_cuda_stream_t stream) {
     if (n < 0 || (n > 0 && (!x || !y))) return fail(FLIC_E_ARG, "bad argument");
     FLIC_CUDA(flic::launch_debug_expf(x, y, n, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_debug_part1(const float* arg, int32_t* y, int64_t n, flic_cuda_stream_t stream) {
+    if (n < 0 || (n > 0 && (!arg || !y))) return fail(FLIC_E_ARG, "bad argument");
+    FLIC_CUDA(flic::launch_debug_part1(arg, y, n, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
 }
@@ -194,14 +202,17 @@ int flic_squeeze(const float* src, float* dst, int64_t batch, int64_t C, int64_t
 struct flic_codec {
     int device;
     int64_t max_symbols, max_streams;
-    // Two pipeline slots; each can hold a chunk of up to slot_symbols symbols / slot_streams streams.
-    static constexpr int kSlots = 2;
+    // A call is cut into chunks of whole streams (at most slot_symbols symbols / slot_streams
+    // streams each) that rotate through kSlots device slots, each with its own CUDA stream: while
+    // chunk c is in its kernels, chunk c+1 is on its way up the PCIe link and chunk c-1 on its
+    // way down, so both copy engines and the SMs are busy at once.
+    static constexpr int kSlots = 3;
     int64_t slot_symbols, slot_streams;
     cudaStream_t streams[kSlots];
     cudaEvent_t done[kSlots];
     struct Slot {
         float *x, *mean, *scale;
-        int64_t* offsets;       // chunk-local stream offsets
+        int64_t* offsets;       // this chunk's slice of the caller's stream offsets (absolute values)
         uint32_t* packed;
         int64_t* word_offsets;
         uint64_t* states;
@@ -209,46 +220,28 @@ struct flic_codec {
         int32_t* status;
         void* workspace;
         int64_t workspace_bytes;
-        int64_t* h_offsets;     // pinned staging: chunk-local offsets / word offsets
-        int64_t* h_word_offsets;
+        int64_t* h_word_offsets;  // pinned staging for the chunk-local word offsets
     } slot[kSlots];
 };
 
-static void codec_free(flic_codec* c) {
-    if (!c) return;
-    cudaSetDevice(c->device);
+static void free_slots(flic_codec* c) {
     for (int i = 0; i < flic_codec::kSlots; ++i) {
         flic_codec::Slot& s = c->slot[i];
         cudaFree(s.x); cudaFree(s.mean); cudaFree(s.scale); cudaFree(s.offsets); cudaFree(s.packed);
         cudaFree(s.word_offsets); cudaFree(s.states); cudaFree(s.end_states); cudaFree(s.status);
         cudaFree(s.workspace);
-        cudaFreeHost(s.h_offsets); cudaFreeHost(s.h_word_offsets);
-        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
-        if (c->done[i]) cudaEventDestroy(c->done[i]);
+        cudaFreeHost(s.h_word_offsets);
+        memset((void*)&s, 0, sizeof s);
     }
-    delete c;
 }
 
-int flic_codec_create(int device, int64_t max_symbols, int64_t max_streams, flic_codec** out) {
-    if (!out || max_symbols < 1 || max_streams < 1) return fail(FLIC_E_ARG, "bad codec size");
-    flic_codec* c = new (std::nothrow) flic_codec();
-    if (!c) return fail(FLIC_E_NOMEM, "out of host memory");
-    memset((void*)c, 0, sizeof *c);
-    c->device = device;
-    c->max_symbols = max_symbols;
-    c->max_streams = max_streams;
-    // A slot holds the whole call when it is small, otherwise ~64 Mi symbols (768 MB of inputs)
-    // so that two chunks in flight overlap copy and compute without a huge footprint.  A single
-    // stream longer than a slot is still accepted by growing the slot to max_symbols.
-    c->slot_symbols = max_symbols;
-    c->slot_streams = max_streams;
-    cudaError_t e = cudaSetDevice(device);
+static cudaError_t alloc_slots(flic_codec* c, int64_t ns, int64_t nt) {
+    c->slot_symbols = ns;
+    c->slot_streams = nt;
+    cudaError_t e = cudaSuccess;
     for (int i = 0; e == cudaSuccess && i < flic_codec::kSlots; ++i) {
         flic_codec::Slot& s = c->slot[i];
-        const int64_t ns = c->slot_symbols, nt = c->slot_streams;
         s.workspace_bytes = flic_encode_workspace_bytes(ns, nt);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&s.x, sizeof(float) * ns);
         if (e == cudaSuccess) e = cudaMalloc(&s.mean, sizeof(float) * ns);
         if (e == cudaSuccess) e = cudaMalloc(&s.scale, sizeof(float) * ns);
@@ -259,9 +252,68 @@ int flic_codec_create(int device, int64_t max_symbols, int64_t max_streams, flic
         if (e == cudaSuccess) e = cudaMalloc(&s.end_states, sizeof(uint64_t) * nt);
         if (e == cudaSuccess) e = cudaMalloc(&s.status, sizeof(int32_t) * nt);
         if (e == cudaSuccess) e = cudaMalloc(&s.workspace, (size_t)s.workspace_bytes);
-        if (e == cudaSuccess) e = cudaMallocHost(&s.h_offsets, sizeof(int64_t) * (nt + 1));
         if (e == cudaSuccess) e = cudaMallocHost(&s.h_word_offsets, sizeof(int64_t) * (nt + 1));
     }
+    return e;
+}
+
+static void codec_free(flic_codec* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_slots(c);
+    for (int i = 0; i < flic_codec::kSlots; ++i) {
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        if (c->done[i]) cudaEventDestroy(c->done[i]);
+    }
+    delete c;
+}
+
+static cudaError_t sync_all(flic_codec* c) {
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < flic_codec::kSlots; ++i) {
+        const cudaError_t ei = cudaStreamSynchronize(c->streams[i]);
+        if (e == cudaSuccess) e = ei;
+    }
+    return e;
+}
+
+// Slots big enough for one stream of `symbols` symbols (a chunk is at least one whole stream).
+static int ensure_slot_symbols(flic_codec* c, int64_t symbols) {
+    if (symbols <= c->slot_symbols) return 0;
+    FLIC_CUDA(sync_all(c));
+    free_slots(c);
+    const cudaError_t e = alloc_slots(c, symbols, c->slot_streams);
+    if (e != cudaSuccess) return cuda_fail(e, "growing codec slots");
+    return 0;
+}
+
+static int64_t chunk_symbols_target() {
+    // 16 Mi symbols per chunk: 192 MB of float inputs (~3.5 ms on a PCIe 5 x16 link) against
+    // ~0.3 ms of kernels, and enough streams per launch (>= 2700 at 6144 symbols) to fill the SMs.
+    const char* env = getenv("FLIC_CODEC_CHUNK_SYMBOLS");
+    if (env) {
+        const long long v = atoll(env);
+        if (v > 0) return (int64_t)v;
+    }
+    return (int64_t)16 << 20;
+}
+
+int flic_codec_create(int device, int64_t max_symbols, int64_t max_streams, flic_codec** out) {
+    if (!out || max_symbols < 1 || max_streams < 1) return fail(FLIC_E_ARG, "bad codec size");
+    flic_codec* c = new (std::nothrow) flic_codec();
+    if (!c) return fail(FLIC_E_NOMEM, "out of host memory");
+    memset((void*)c, 0, sizeof *c);
+    c->device = device;
+    c->max_symbols = max_symbols;
+    c->max_streams = max_streams;
+    const int64_t target = chunk_symbols_target();
+    cudaError_t e = cudaSetDevice(device);
+    for (int i = 0; e == cudaSuccess && i < flic_codec::kSlots; ++i) {
+        e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess)
+        e = alloc_slots(c, max_symbols < target ? max_symbols : target, max_streams < (1 << 20) ? max_streams : (1 << 20));
     if (e != cudaSuccess) {
         codec_free(c);
         return cuda_fail(e, "flic_codec_create");
@@ -289,6 +341,18 @@ static int check_offsets(const int64_t* off, int64_t n_streams) {
     return 0;
 }
 
+// Last stream (exclusive) of the chunk that starts at s0: as many whole streams as fit a slot.
+// Returns s0 when the first stream alone is larger than a slot.
+static int64_t chunk_end(const flic_codec* c, const int64_t* off, int64_t n_streams, int64_t s0) {
+    int64_t lo = s0, hi = n_streams < s0 + c->slot_streams ? n_streams : s0 + c->slot_streams;
+    const int64_t limit = off[s0] + c->slot_symbols;
+    while (lo < hi) {  // largest s1 in (s0, hi] with off[s1] <= limit
+        const int64_t mid = lo + (hi - lo + 1) / 2;
+        if (off[mid] <= limit) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const float* scale,
                       const int64_t* stream_offsets, int64_t n_streams, uint32_t* words_out,
                       int64_t words_capacity, int64_t* word_offsets_out, uint64_t* states_out,
@@ -305,28 +369,68 @@ int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const fl
     if (!states_out || !status_out || (n_symbols > 0 && (!x || !mean || !scale || !words_out)))
         return fail(FLIC_E_ARG, "null pointer");
     FLIC_CUDA(cudaSetDevice(c->device));
-    flic_codec::Slot& s = c->slot[0];
-    cudaStream_t st = c->streams[0];
-    FLIC_CUDA(cudaMemcpyAsync(s.x, x, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.mean, mean, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.scale, scale, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.offsets, stream_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyHostToDevice, st));
-    if (int rc = flic_rans_encode(s.x, s.mean, s.scale, s.offsets, n_streams, n_symbols, nullptr, s.workspace,
-                                  s.workspace_bytes, s.packed, n_symbols > 0 ? n_symbols : 1, s.word_offsets,
-                                  s.states, s.status, st))
-        return rc;
-    FLIC_CUDA(cudaMemcpyAsync(word_offsets_out, s.word_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaMemcpyAsync(states_out, s.states, sizeof(uint64_t) * n_streams, cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaMemcpyAsync(status_out, s.status, sizeof(int32_t) * n_streams, cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaStreamSynchronize(st));
-    const int64_t total = word_offsets_out[n_streams];
-    if (n_words_out) *n_words_out = total;
-    if (total > words_capacity)
-        return fail(FLIC_E_CAPACITY, "words_out holds %lld words, %lld needed", (long long)words_capacity, (long long)total);
-    if (total > 0) {
-        FLIC_CUDA(cudaMemcpyAsync(words_out, s.packed, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
-        FLIC_CUDA(cudaStreamSynchronize(st));
+
+    const int64_t* off = stream_offsets;
+    int64_t total_words = 0;       // words of all finalised chunks
+    bool overflow = false;
+    struct Pending { int slot; int64_t s0, s1; bool active; } prev = {0, 0, 0, false};
+
+    // Second half of a chunk: its word counts are on the host now, so the words can be copied to
+    // their final place and the caller's word offsets filled in.
+    auto finalize = [&](const Pending& p) -> int {
+        flic_codec::Slot& sl = c->slot[p.slot];
+        FLIC_CUDA(cudaEventSynchronize(c->done[p.slot]));
+        const int64_t ns = p.s1 - p.s0;
+        const int64_t* hw = sl.h_word_offsets;
+        const int64_t chunk_words = hw[ns];
+        for (int64_t i = 1; i <= ns; ++i) word_offsets_out[p.s0 + i] = total_words + hw[i];
+        if (total_words + chunk_words > words_capacity) overflow = true;
+        else if (chunk_words > 0)
+            FLIC_CUDA(cudaMemcpyAsync(words_out + total_words, sl.packed, sizeof(uint32_t) * chunk_words,
+                                      cudaMemcpyDeviceToHost, c->streams[p.slot]));
+        total_words += chunk_words;
+        return 0;
+    };
+
+    int64_t s0 = 0;
+    for (int64_t chunk = 0; s0 < n_streams; ++chunk) {
+        int64_t s1 = chunk_end(c, off, n_streams, s0);
+        if (s1 == s0) {  // one stream larger than a slot: finish what is in flight, grow, retry
+            if (prev.active) { if (int rc = finalize(prev)) return rc; prev.active = false; }
+            if (int rc = ensure_slot_symbols(c, off[s0 + 1] - off[s0])) return rc;
+            s1 = chunk_end(c, off, n_streams, s0);
+        }
+        const int slot = (int)(chunk % flic_codec::kSlots);
+        flic_codec::Slot& sl = c->slot[slot];
+        cudaStream_t st = c->streams[slot];
+        const int64_t a = off[s0], n = off[s1] - a, ns = s1 - s0;
+        if (n > 0) {
+            FLIC_CUDA(cudaMemcpyAsync(sl.x, x + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+            FLIC_CUDA(cudaMemcpyAsync(sl.mean, mean + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+            FLIC_CUDA(cudaMemcpyAsync(sl.scale, scale + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+        }
+        FLIC_CUDA(cudaMemcpyAsync(sl.offsets, off + s0, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+        // the kernels index symbols (and the scratch region) by the caller's absolute offsets
+        const EncodeWorkspace w = carve(sl.workspace, c->slot_symbols, c->slot_streams);
+        FLIC_CUDA(flic::launch_rans_encode(sl.x - a, sl.mean - a, sl.scale - a, sl.offsets, ns, nullptr, w.scratch - a,
+                                           w.counts, sl.states, sl.status, st));
+        FLIC_CUDA(flic::launch_scan_counts(w.counts, ns, sl.word_offsets, w.scan_tmp, st));
+        FLIC_CUDA(flic::launch_pack_words(w.scratch - a, sl.offsets, sl.word_offsets, ns, sl.packed, c->slot_symbols,
+                                          sl.status, st));
+        g_launches += 5;
+        FLIC_CUDA(cudaMemcpyAsync(sl.h_word_offsets, sl.word_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyDeviceToHost, st));
+        FLIC_CUDA(cudaMemcpyAsync(states_out + s0, sl.states, sizeof(uint64_t) * ns, cudaMemcpyDeviceToHost, st));
+        FLIC_CUDA(cudaMemcpyAsync(status_out + s0, sl.status, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+        FLIC_CUDA(cudaEventRecord(c->done[slot], st));
+        if (prev.active) { if (int rc = finalize(prev)) return rc; }
+        prev = {slot, s0, s1, true};
+        s0 = s1;
     }
+    if (prev.active) { if (int rc = finalize(prev)) return rc; }
+    FLIC_CUDA(sync_all(c));
+    if (n_words_out) *n_words_out = total_words;
+    if (overflow)
+        return fail(FLIC_E_CAPACITY, "words_out holds %lld words, %lld needed", (long long)words_capacity, (long long)total_words);
     return 0;
 }
 
@@ -346,26 +450,41 @@ int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_
     if (!states || !status_out || (n_symbols > 0 && (!mean || !scale || !x_out)) || (n_words > 0 && !words))
         return fail(FLIC_E_ARG, "null pointer");
     FLIC_CUDA(cudaSetDevice(c->device));
-    flic_codec::Slot& s = c->slot[0];
-    cudaStream_t st = c->streams[0];
-    if (n_words > 0)
-        FLIC_CUDA(cudaMemcpyAsync(s.packed, words, sizeof(uint32_t) * n_words, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.word_offsets, word_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.states, states, sizeof(uint64_t) * n_streams, cudaMemcpyHostToDevice, st));
-    if (n_symbols > 0) {
-        FLIC_CUDA(cudaMemcpyAsync(s.mean, mean, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
-        FLIC_CUDA(cudaMemcpyAsync(s.scale, scale, sizeof(float) * n_symbols, cudaMemcpyHostToDevice, st));
+    const int64_t* off = stream_offsets;
+    int64_t s0 = 0;
+    for (int64_t chunk = 0; s0 < n_streams; ++chunk) {
+        int64_t s1 = chunk_end(c, off, n_streams, s0);
+        if (s1 == s0) {
+            if (int rc = ensure_slot_symbols(c, off[s0 + 1] - off[s0])) return rc;
+            s1 = chunk_end(c, off, n_streams, s0);
+        }
+        const int64_t a = off[s0], n = off[s1] - a, ns = s1 - s0;
+        const int64_t wa = word_offsets[s0], nw = word_offsets[s1] - wa;
+        if (nw > c->slot_symbols) {  // a valid stream never has more words than symbols
+            if (int rc = ensure_slot_symbols(c, nw)) return rc;
+        }
+        const int slot = (int)(chunk % flic_codec::kSlots);
+        flic_codec::Slot& sl = c->slot[slot];
+        cudaStream_t st = c->streams[slot];
+        if (nw > 0) FLIC_CUDA(cudaMemcpyAsync(sl.packed, words + wa, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
+        FLIC_CUDA(cudaMemcpyAsync(sl.word_offsets, word_offsets + s0, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+        FLIC_CUDA(cudaMemcpyAsync(sl.states, states + s0, sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, st));
+        if (n > 0) {
+            FLIC_CUDA(cudaMemcpyAsync(sl.mean, mean + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+            FLIC_CUDA(cudaMemcpyAsync(sl.scale, scale + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+        }
+        FLIC_CUDA(cudaMemcpyAsync(sl.offsets, off + s0, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+        // absolute symbol and word offsets index shifted base pointers
+        FLIC_CUDA(flic::launch_rans_decode(sl.packed - wa, sl.word_offsets, sl.states, sl.mean - a, sl.scale - a,
+                                           sl.offsets, ns, sl.x - a, sl.end_states, sl.status, 1, st));
+        g_launches += 1;
+        if (n > 0) FLIC_CUDA(cudaMemcpyAsync(x_out + a, sl.x, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        if (end_states_out)
+            FLIC_CUDA(cudaMemcpyAsync(end_states_out + s0, sl.end_states, sizeof(uint64_t) * ns, cudaMemcpyDeviceToHost, st));
+        FLIC_CUDA(cudaMemcpyAsync(status_out + s0, sl.status, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+        s0 = s1;
     }
-    FLIC_CUDA(cudaMemcpyAsync(s.offsets, stream_offsets, sizeof(int64_t) * (n_streams + 1), cudaMemcpyHostToDevice, st));
-    if (int rc = flic_rans_decode(s.packed, s.word_offsets, s.states, s.mean, s.scale, s.offsets, n_streams, s.x,
-                                  s.end_states, s.status, 1, st))
-        return rc;
-    if (n_symbols > 0)
-        FLIC_CUDA(cudaMemcpyAsync(x_out, s.x, sizeof(float) * n_symbols, cudaMemcpyDeviceToHost, st));
-    if (end_states_out)
-        FLIC_CUDA(cudaMemcpyAsync(end_states_out, s.end_states, sizeof(uint64_t) * n_streams, cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaMemcpyAsync(status_out, s.status, sizeof(int32_t) * n_streams, cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaStreamSynchronize(st));
+    FLIC_CUDA(sync_all(c));
     return 0;
 }
 
@@ -380,6 +499,7 @@ int flic_rans_encode_single(flic_codec* c, uint64_t state, int64_t n, const floa
     if (n == 0) return 0;
     if (!x || !mean || !scale || !buffer_out) return fail(FLIC_E_ARG, "null pointer");
     FLIC_CUDA(cudaSetDevice(c->device));
+    if (int rc = ensure_slot_symbols(c, n)) return rc;
     flic_codec::Slot& s = c->slot[0];
     cudaStream_t st = c->streams[0];
     const int64_t offs[2] = {0, n};
@@ -432,6 +552,7 @@ int flic_rans_decode_single(flic_codec* c, uint64_t state, const uint32_t* buffe
     int32_t status = 0;
     int rc = 0;
     cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess && ensure_slot_symbols(c, n > n_buffer ? n : n_buffer) != 0) { free(fm); free(fb); return FLIC_E_NOMEM; }
     flic_codec::Slot& s = c->slot[0];
     cudaStream_t st = c->streams[0];
     if (e == cudaSuccess && n_buffer > 0) e = cudaMemcpyAsync(s.packed, fb, sizeof(uint32_t) * n_buffer, cudaMemcpyHostToDevice, st);

@@ -47,6 +47,26 @@ debug_expf_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n)
         y[i] = expf_glibc(x[i], s_tab);
 }
 
+// Diagnostic: part1 as a function of the float argument alone (the quotient stage replaced by a
+// plain widening), for the exhaustive sweep against the reference arithmetic.
+__global__ void __launch_bounds__(256)
+debug_part1_kernel(const float* __restrict__ arg, int32_t* __restrict__ y, int64_t n) {
+    __shared__ uint64_t s_tab[32];
+    stage_exp_table(s_tab);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = part1_from_arg(arg_from_quotient((double)arg[i]), s_tab);
+}
+
+cudaError_t launch_debug_part1(const float* arg, int32_t* y, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    debug_part1_kernel<<<(unsigned)blocks, 256, 0, stream>>>(arg, y, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_debug_expf(const float* x, float* y, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     int64_t blocks = (n + 255) / 256;

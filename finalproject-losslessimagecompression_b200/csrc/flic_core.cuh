@@ -351,13 +351,10 @@ FLIC_HD double div_by_scale(double a, const SymbolModel& m) {
 #ifndef FLIC_V_XU
 #define FLIC_V_XU 1
 #endif
-FLIC_HD int part1_at(double a, const SymbolModel& m, const uint64_t* tab) {
-    const double t4 = dsub(a, m.mean_d);
-#if FLIC_ARG_XU
-    const double arg = (double)fminf(fmaxf(d2f(div_by_scale(t4, m)), -128.0f), 128.0f);
-#else
-    const double arg = round24(clamp_mag128(div_by_scale(t4, m)));
-#endif
+// Everything after the argument: arg is (double)(float)arg_f with |arg| <= 128 (or <= 128.001 from
+// the FP64-pipe rounding).  A pure function of a 32-bit float, so it is swept exhaustively
+// against the reference arithmetic on the GPU (tests/test_gpu_flow.py, flic_debug_part1).
+FLIC_HD int part1_from_arg(double arg, const uint64_t* tab) {
 #if FLIC_E_XU
     const double e = (double)fminf(d2f(exp_core(arg, tab, true)), 3.402823466e+38f);
 #else
@@ -370,6 +367,20 @@ FLIC_HD int part1_at(double a, const SymbolModel& m, const uint64_t* tab) {
     const double v = round24(dmul(p, kPart1Scale));
     return (int)floor_nonneg_u32(dadd(v, 0.5));  // roundf of a non-negative float: floor(v + 0.5), exact sum
 #endif
+}
+
+// The quotient q = t4 / scale rounded to float and limited to [-128, 128].
+FLIC_HD double arg_from_quotient(double q) {
+#if FLIC_ARG_XU
+    return (double)fminf(fmaxf(d2f(q), -128.0f), 128.0f);
+#else
+    return round24(clamp_mag128(q));
+#endif
+}
+
+FLIC_HD int part1_at(double a, const SymbolModel& m, const uint64_t* tab) {
+    const double t4 = dsub(a, m.mean_d);
+    return part1_from_arg(arg_from_quotient(div_by_scale(t4, m)), tab);
 }
 
 // (double)xq + 1/512 = (2 s + 1) / 512 exactly, built without a conversion: the bits of

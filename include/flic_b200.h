@@ -71,6 +71,11 @@ int flic_cdf_tables(const float* x, const float* mean, const float* scale, int64
  * reference links it, expf@GLIBC_2.27, rans/rans.cpp:1301).  Lets a test sweep it against libm. */
 int flic_debug_expf(const float* x, float* y, int64_t n, flic_cuda_stream_t stream);
 
+/* Diagnostic: y[i] = part1 of CDF() for the float argument arg[i] alone, i.e.
+ * (int) roundf((float)(logistic(arg) * 16775168)) of rans/rans.pyx:25-26,34 -- every operation
+ * of CDF() after the division.  A function of 32 bits, so tests sweep all of them. */
+int flic_debug_part1(const float* arg, int32_t* y, int64_t n, flic_cuda_stream_t stream);
+
 /* Bytes of device workspace flic_rans_encode needs (worst-case word scratch + scan temporaries). */
 int64_t flic_encode_workspace_bytes(int64_t n_symbols, int64_t n_streams);
 

@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
         L.flic_oracle_expf_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_int, u32p, C.c_uint32]
         L.flic_oracle_expf_compare.restype = None
         L.flic_oracle_expf_compare.argtypes = [C.c_uint32, C.c_int64, f32p, u64p, u64p, u32p, C.c_uint32]
+        L.flic_oracle_part1_compare.restype = None
+        L.flic_oracle_part1_compare.argtypes = [C.c_uint32, C.c_int64, i32p, u64p, u32p, C.c_uint32]
         L.flic_oracle_cdf.restype = C.c_int
         L.flic_oracle_cdf.argtypes = [C.c_float] * 4
         L.flic_oracle_lower.restype = C.c_int
@@ -183,6 +185,16 @@ def expf_compare(lo_bits: int, got: np.ndarray, max_bad: int = 16):
     lib().flic_oracle_expf_compare(lo_bits, got.size, _p(got, C.c_float), C.byref(bh), C.byref(br),
                                    _p(bad, C.c_uint32), max_bad)
     return int(bh.value), int(br.value), bad[: min(int(bh.value), max_bad)].copy()
+
+
+def part1_compare(lo_bits: int, got: np.ndarray, max_bad: int = 16):
+    """got[i] = candidate part1 for the float argument with bit pattern lo_bits+i (rans.pyx:25-26,34).
+    Returns (mismatches vs the reference arithmetic with the host libm, first bad bit patterns)."""
+    got = np.ascontiguousarray(got, dtype=np.int32)
+    b = C.c_uint64(0)
+    bad = np.zeros(max_bad, np.uint32)
+    lib().flic_oracle_part1_compare(lo_bits, got.size, _p(got, C.c_int32), C.byref(b), _p(bad, C.c_uint32), max_bad)
+    return int(b.value), bad[: min(int(b.value), max_bad)].copy()
 
 
 # ---- the reference's own Cython module, rebuilt (oracle/_ref) -------------------------------

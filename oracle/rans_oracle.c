@@ -162,6 +162,28 @@ static inline int cdf_ref(float x, float mean, float scale, float lower, int *er
     return part1 + part2;
 }
 
+/* got[i] is some implementation's part1 for the float argument with bit pattern lo_bits + i:
+ * (int) roundf((float)(logistic(arg) * 16775168.0)), rans/rans.pyx:25-26,34 with the promotions of
+ * rans.cpp:1301-1306,1441-1449.  Counts disagreements; NaN arguments are skipped. */
+void flic_oracle_part1_compare(uint32_t lo_bits, int64_t n, const int32_t *got, uint64_t *bad,
+                               uint32_t *first_bad, uint32_t max_bad)
+{
+    uint64_t b = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t u = lo_bits + (uint32_t)i;
+        float arg;
+        memcpy(&arg, &u, 4);
+        if (arg != arg) continue;
+        double prod = logistic_f(arg) * 16775168.0;
+        int want = (int)roundf((float)prod);
+        if (got[i] != want) {
+            if (b < max_bad) first_bad[b] = u;
+            ++b;
+        }
+    }
+    *bad = b;
+}
+
 int flic_oracle_cdf(float x, float mean, float scale, float lower)
 {
     int err = 0;

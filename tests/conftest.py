@@ -55,6 +55,7 @@ def host_harness():
     H.hh_expf.restype = C.c_float
     H.hh_expf.argtypes = [C.c_float]
     H.hh_lower.argtypes = [C.c_float]
+    H.hh_part1.argtypes = [C.c_float]
     H.hh_cdf.argtypes = [C.c_int, C.c_float, C.c_float]
     H.hh_tables.argtypes = [f32p, f32p, f32p, C.c_int64, u32p, u32p]
     H.hh_encode.argtypes = [f32p, f32p, f32p, C.c_int64, u32p, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]

@@ -27,6 +27,8 @@ void hh_expf_array(uint32_t lo_bits, int64_t n, float* out) {
 
 int hh_lower(float mean) { return lower_of(mean); }
 
+int hh_part1(float arg) { return part1_from_arg(arg_from_quotient((double)arg), kTab); }
+
 int hh_cdf(int s, float mean, float scale) {
     SymbolModel m = make_model(mean, scale);
     return cdf_at(s, m, kTab);

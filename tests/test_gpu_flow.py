@@ -371,3 +371,62 @@ def test_device_expf_exhaustive_against_host_libm(oracle):
                     firsts += first.tolist()
     assert bad_rest == 0
     assert set(firsts) <= {0x4202422f, 0xc27c65d9} and bad_host <= 2
+
+
+@pytest.mark.parametrize("chunk", [4096, 70_000])
+def test_host_codec_chunked_pipeline(oracle, monkeypatch, chunk):
+    """A call larger than one slot is cut into chunks of whole streams that rotate through the
+    codec's slots; the result must not depend on where the cuts fall.  One stream is longer than a
+    slot (the slots grow), some are empty, and the partition is ragged."""
+    from flic_b200 import rans
+    monkeypatch.setenv("FLIC_CODEC_CHUNK_SYMBOLS", str(chunk))
+    n = 260_000
+    x, mean, scale = gen("test", n, 31)
+    rng = np.random.default_rng(7)
+    cuts = np.sort(rng.integers(0, n - 90_000, 300))
+    off = np.concatenate([[0], cuts, cuts[-1:], [cuts[-1] + 90_000], [n]]).astype(np.int64)   # empty + 90k-symbol streams
+    ns = off.size - 1
+    codec = rans.HostCodec(n, ns)
+    words, woff, states, status = codec.encode(x, mean, scale, off)
+    assert not status.any()
+    w_o, wo_o, st_o, _ = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+    assert np.array_equal(words, w_o) and np.array_equal(woff, wo_o) and np.array_equal(states, st_o)
+    rec, end, status = codec.decode(words, woff, states, mean, scale, off)
+    assert not status.any() and np.array_equal(rec, x)
+    assert (end == (1 << 32)).all()
+    # single-stream drop-ins still work on the same codec after the slots grew
+    st1, buf1 = codec.encode_single(1 << 32, 50_000, x[:50_000], mean[:50_000], scale[:50_000])
+    st_ref, buf_ref = oracle.encode(1 << 32, 50_000, x[:50_000], mean[:50_000], scale[:50_000])
+    assert st1 == st_ref and np.array_equal(buf1, buf_ref)
+    codec.close()
+
+
+def test_device_part1_exhaustive_over_every_float_argument(oracle):
+    """part1 of CDF() is a function of the float argument alone once the division is done
+    (rans.pyx:25-26,34).  Sweep every non-NaN float (4.28e9 arguments, both infinities included):
+    the device chain -- glibc-expf body, roundings on the FP64 pipe or by conversion, reciprocal,
+    scaling, roundf -- must give the integer the reference arithmetic gives with this host's libm."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    from flic_b200 import _lib
+    L = _lib.lib()
+    chunk = 1 << 27
+    parts = min(16, max(4, len(os.sched_getaffinity(0))))
+    bad, firsts = 0, []
+    for base in (0, 0x80000000):
+        for lo in range(0, 0x7f800001, chunk):          # up to and including +/-inf
+            n = min(chunk, 0x7f800001 - lo)
+            bits = torch.arange(base + lo, base + lo + n, dtype=torch.int64, device="cuda").to(torch.int32)
+            y = torch.empty(n, dtype=torch.int32, device="cuda")
+            _lib.check(L.flic_debug_part1(bits.view(torch.float32).data_ptr(), y.data_ptr(), n, None))
+            got = y.cpu().numpy()
+            step = (n + parts - 1) // parts
+
+            def run(k):
+                a, b = k * step, min((k + 1) * step, n)
+                return oracle.part1_compare(base + lo + a, got[a:b]) if a < b else (0, np.zeros(0, np.uint32))
+            with ThreadPoolExecutor(parts) as ex:
+                for b_, first in ex.map(run, range(parts)):
+                    bad += b_
+                    firsts += first.tolist()
+    assert bad == 0, [hex(f) for f in firsts[:16]]
