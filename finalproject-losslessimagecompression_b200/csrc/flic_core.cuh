@@ -76,21 +76,49 @@ FLIC_HD double dfma(double a, double b, double c) {
     return fma(a, b, c);
 #endif
 }
-// Correctly rounded reciprocal.  On the device this is the fast path of CUDA's own __drcp_rn
-// (MUFU.RCP64H seed, e = 1 - a y, y += y (e + e^2), one more fma correction) WITHOUT its
-// exponent-range test and slow-path call: every operand this file feeds it is a normal double
-// with an exponent far from the extremes -- a float widened to double (2^-149 .. 2^128),
-// 1 + e with e in [0, FLT_MAX], or an integer frequency in [1, 2^24] -- so the test can never
-// fire.  tests/ compare it with __drcp_rn on the device over those ranges.
-FLIC_HD double drcp(double a) {
+// Reciprocals.  The hardware seed (MUFU.RCP64H) looks at the high word of its operand only, so its
+// relative error e0 is up to ~2^-20; every operand this file feeds it is a normal double with an
+// exponent far from the extremes -- a float widened to double (2^-149 .. 2^128), 1 + e with
+// e in [0, 2^185], or an integer frequency in [1, 2^24] -- so no range test is needed.
+//
+// rcp_cubic: seed, then y (1 + e + e^2) with e = 1 - a y: relative error ~ e0^3 + 2^-53 < 2^-52.
+// Enough wherever the quotient built from it is corrected with an exact remainder (div_by_scale,
+// rans_push).
+FLIC_HD double rcp_cubic(double a) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     double e = __fma_rn(-a, y, 1.0);
     e = __fma_rn(e, e, e);
+    return __fma_rn(y, e, y);
+#else
+    return 1.0 / a;
+#endif
+}
+// drcp: stands in for the reference's correctly rounded `1.0 / a` in part1_from_arg().  It is the
+// same cubic step, whose result is RN of a value within ~2^-58 (relative) of 1/a -- the correctly
+// rounded reciprocal except when 1/a lies that close to a rounding boundary, and then one ulp
+// off.  One ulp of p moves p * 16775168 by at most one ulp, which changes part1 only if that
+// product sits on a float rounding boundary to within 2^-52.  part1_from_arg() is a function of
+// one 32-bit float, and the exhaustive sweep of all 2^32 of them against the reference
+// arithmetic (tests/test_gpu_flow.py::test_device_part1_exhaustive_over_every_float_argument)
+// shows that this never happens: the shorter sequence is exact for every input that exists.
+#ifndef FLIC_DRCP_STEPS
+#define FLIC_DRCP_STEPS 3
+#endif
+FLIC_HD double drcp(double a) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = __fma_rn(-a, y, 1.0);
+#if FLIC_DRCP_STEPS == 3
+    e = __fma_rn(e, e, e);
+    return __fma_rn(y, e, y);
+#else
     y = __fma_rn(y, e, y);
     e = __fma_rn(-a, y, 1.0);
     return __fma_rn(y, e, y);
+#endif
 #else
     return 1.0 / a;
 #endif
@@ -130,6 +158,29 @@ FLIC_HD double bits_f64(uint64_t u) {
     return __longlong_as_double((long long)u);
 #else
     double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+// high / low 32-bit words of a double, and back: register renaming on the device, so integer
+// work on the exponent field costs 32-bit instructions without carry chains
+FLIC_HD uint32_t f64_hi(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2hiint(d);
+#else
+    return (uint32_t)(f64_bits(d) >> 32);
+#endif
+}
+FLIC_HD uint32_t f64_lo(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(d);
+#else
+    return (uint32_t)f64_bits(d);
+#endif
+}
+FLIC_HD double f64_from_words(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    return bits_f64(((uint64_t)hi << 32) | lo);
 #endif
 }
 FLIC_HD uint32_t f32_bits(float f) {
@@ -176,8 +227,7 @@ FLIC_HD int d2i_rz(double v) {
 // Differences from the conversion pair: no overflow to inf and no subnormal range.  Callers show
 // that both only occur where part1 is saturated anyway (see part1_at).
 FLIC_HD double round24(double v) {
-    const uint64_t b = f64_bits(v);
-    const double M = bits_f64((b & 0x7ff0000000000000ull) + 0x01d8000000000000ull);
+    const double M = f64_from_words((f64_hi(v) & 0x7ff00000u) + 0x01d80000u, 0u);
     return dsub(dadd(v, M), M);
 }
 
@@ -209,11 +259,10 @@ FLIC_HD double u64_to_f64(uint32_t hi, uint32_t lo) {
 // q with its magnitude limited to [0, 128 (1 + 2^-20)): beyond |q| = 128 the caller's result is
 // saturated and only the sign matters.  Integer min on the high word; NaN becomes finite too.
 FLIC_HD double clamp_mag128(double q) {
-    const uint64_t b = f64_bits(q);
-    const uint32_t hi = (uint32_t)(b >> 32);
+    const uint32_t hi = f64_hi(q);
     uint32_t ah = hi & 0x7fffffffu;
     ah = ah < 0x40600000u ? ah : 0x40600000u;
-    return bits_f64(((uint64_t)(ah | (hi & 0x80000000u)) << 32) | (uint32_t)b);
+    return f64_from_words(ah | (hi & 0x80000000u), f64_lo(q));
 }
 
 // ---- glibc expf ---------------------------------------------------------------------------------
@@ -246,11 +295,12 @@ FLIC_HD double exp_core(double xd, const uint64_t* tab, bool neg) {
     const double C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
     const double z = dmul(neg ? -InvLn2N : InvLn2N, xd);
     double kd = dadd(z, Shift);
-    const uint64_t ki = f64_bits(kd);
+    const uint32_t ki = f64_lo(kd);          // k mod 2^32 sits in the low mantissa bits
     kd = dsub(kd, Shift);
     const double r = dsub(z, kd);
-    const uint64_t t = tab[ki & 31] + (ki << 47);
-    const double s = bits_f64(t);
+    // T[k % 32] + (k << 47): the shift only reaches the high word (47 - 32 = 15)
+    const uint64_t tv = tab[ki & 31];
+    const double s = f64_from_words((uint32_t)(tv >> 32) + (ki << 15), (uint32_t)tv);
     const double zz = dfma(C0, r, C1);
     const double r2 = dmul(r, r);
     double y = dfma(C2, r, 1.0);
@@ -284,7 +334,7 @@ FLIC_HD int lower_of(float mean) { return lower_of_d((double)mean); }
 struct SymbolModel {
     double mean_d;   // (double)mean
     double scale_d;  // (double)scale
-    double rscale;   // RN(1 / scale_d)
+    double rscale;   // 1 / scale_d to within 2^-52 relative
     int lower;       // window origin in 1/256 units
 };
 
@@ -308,16 +358,20 @@ FLIC_HD SymbolModel make_model(float mean, float scale) {
     SymbolModel m;
     m.mean_d = (double)mean;
     m.scale_d = (double)scale;
-    m.rscale = drcp(m.scale_d);
+    m.rscale = rcp_cubic(m.scale_d);
     m.lower = lower_of_d(m.mean_d);
     return m;
 }
 
-// Correctly rounded a / b from r = RN(1/b) (Markstein): q0 = RN(a r); e = a - b q0 (exact, fma);
-// q = RN(q0 + e r).  Valid here because b is a float widened to double (never an all-ones
-// significand), a and b are far from the double over/underflow thresholds, and r is the
-// correctly rounded reciprocal.  tests/ compares it with IEEE division on the host (millions of
-// cases) and on the device against __ddiv_rn.
+// Correctly rounded a / b from r ~ 1/b (relative error eps < 2^-52): q0 = RN(a r);
+// rem = a - b q0 (exact, fma); q = RN(q0 + rem r).  The value rounded in the last step is
+// Q + (Q - q0) eps' with Q = a / b, |Q - q0| <= 2^-51 |Q| and |eps'| < 2^-52, i.e. within 2^-103
+// (relative) of Q.  b is a float widened to double (24-bit significand), and a quotient of a
+// 53-bit by a 24-bit significand is either exactly representable (b a power of two) or at least
+// 2^-78 (relative) away from every double and every midpoint between doubles (|a 2^k - m b| >= 1
+// for integers), so no rounding boundary can fall in between: q = RN(a / b).  No intermediate can
+// over/underflow for the operand ranges of this file.  tests/ compares it with IEEE division on
+// the host (millions of cases) and every table / bitstream parity test exercises it on the device.
 FLIC_HD double div_by_scale(double a, const SymbolModel& m) {
     const double q0 = dmul(a, m.rscale);
     const double e = dfma(-q0, m.scale_d, a);
@@ -339,7 +393,7 @@ FLIC_HD double div_by_scale(double a, const SymbolModel& m) {
 //     both round to 0.
 // Which of the three float roundings use the conversion instructions (XU pipe) and which the
 // FP64-pipe round24().  All eight combinations give identical tables (tools/variant_bench.cu);
-// measured on B200, K1 runs 142 / 149 / 155 / 156 G symbols/s for 000 / 001 / 101 / 111: the
+// measured on B200, K1 runs 152 / 161 / 169 / 163 G symbols/s for 000 / 001 / 101 / 111: the
 // XU pipe (8 cycles per warp-instruction) and the FP64 pipe (2 cycles) overlap, so the work is
 // split between them.
 #ifndef FLIC_ARG_XU
