@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libflic_b200.so")
+# FLIC_B200_LIB selects another build of the same library (kernel experiments); default: in-tree
+LIB_PATH = os.environ.get("FLIC_B200_LIB") or os.path.join(HERE, "libflic_b200.so")
 
 # status bits (include/flic_b200.h)
 ST_ZERO_SCALE = 1
@@ -34,6 +35,8 @@ SIGNATURES = {
     "flic_cdf_tables": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_debug_expf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "flic_debug_part1": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "flic_dlogistic_log_prob": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, C.c_float, _vp, _vp, _vp]),
+    "flic_dlogistic_sample": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp]),
     "flic_encode_workspace_bytes": (_i64, [_i64, _i64]),
     "flic_rans_encode": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_rans_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp]),

@@ -195,6 +195,29 @@ int flic_squeeze(const float* src, float* dst, int64_t batch, int64_t C, int64_t
     return 0;
 }
 
+int flic_dlogistic_log_prob(const float* x, const float* mean, const float* logscale, int64_t batch,
+                            int64_t per_item, int nbits, float eps, float* logp_out, float* sum_out,
+                            flic_cuda_stream_t stream) {
+    if (batch < 0 || per_item < 0 || nbits < 0 || nbits > 23) return fail(FLIC_E_ARG, "bad argument");
+    if (batch == 0) return 0;
+    if (batch > 0x7fffffffll) return fail(FLIC_E_ARG, "batch too large");
+    if ((per_item > 0 && (!x || !mean || !logscale)) || (!logp_out && !sum_out)) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_dlogistic_log_prob(x, mean, logscale, batch, per_item, nbits, eps, logp_out, sum_out,
+                                              (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_dlogistic_sample(const float* u, const float* mean, const float* logscale, int64_t n, int nbits,
+                          float* out, flic_cuda_stream_t stream) {
+    if (n < 0 || nbits < 0 || nbits > 23) return fail(FLIC_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    if (!u || !mean || !logscale || !out) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_dlogistic_sample(u, mean, logscale, n, nbits, out, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Host entry points
  * ------------------------------------------------------------------------------------------ */

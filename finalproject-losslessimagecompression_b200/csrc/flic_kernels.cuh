@@ -60,4 +60,12 @@ cudaError_t launch_permute_channels(const float* src, float* dst, const int32_t*
 cudaError_t launch_squeeze(const float* src, float* dst, int64_t batch, int64_t C, int64_t H,
                            int64_t W, int scale, int direction, cudaStream_t stream);
 
+// N4: DLogistic.log_prob with the per-image sum fused (distlib.py:40-55, flows.py:154-169) and
+// DLogistic.sample from given uniforms (distlib.py:57-70).  logp_out / sum_out may be null.
+cudaError_t launch_dlogistic_log_prob(const float* x, const float* mean, const float* logscale,
+                                      int64_t batch, int64_t per_item, int nbits, float eps,
+                                      float* logp_out, float* sum_out, cudaStream_t stream);
+cudaError_t launch_dlogistic_sample(const float* u, const float* mean, const float* logscale, int64_t n,
+                                    int nbits, float* out, cudaStream_t stream);
+
 }  // namespace flic

@@ -40,8 +40,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+#ifndef FLIC_DEC_MIN_BLOCKS
+#define FLIC_DEC_MIN_BLOCKS 8
+#endif
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? FLIC_DEC_MIN_BLOCKS : 16)
 rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ word_offsets,
                    const uint64_t* __restrict__ states, const float* __restrict__ mean,
                    const float* __restrict__ scale, const int64_t* __restrict__ offsets,

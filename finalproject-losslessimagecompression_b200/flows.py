@@ -193,12 +193,20 @@ class IDFlows(nn.Module):
         return x
 
     def log_likelihood(self, latents, means, logscales):
+        """flows.py:154-169.  On CUDA without autograd each level is one fused kernel
+        (evaluation + per-image sum, DLogistic.log_prob_sums); the per-level means are the sums
+        divided by the level's element count."""
         log_Ps = []
         log_prob = torch.zeros(latents[0].shape[0], device=latents[0].device)
         for z, mean, logscale in zip(latents, means, logscales):
-            logp = self.dist.log_prob(z, mean, logscale, self.nbits)
-            log_Ps.append(torch.mean(logp, dim=(1, 2, 3)))
-            log_prob = log_prob + torch.sum(logp, dim=(1, 2, 3))
+            if hasattr(self.dist, "log_prob_sums"):
+                sums = self.dist.log_prob_sums(z, mean, logscale, self.nbits)
+                log_Ps.append(sums / (z.numel() // z.shape[0]))
+            else:
+                logp = self.dist.log_prob(z, mean, logscale, self.nbits)
+                log_Ps.append(torch.mean(logp, dim=(1, 2, 3)))
+                sums = torch.sum(logp, dim=(1, 2, 3))
+            log_prob = log_prob + sums
         return log_prob / (self.H * self.W * self.C), log_Ps
 
     def inverse(self):
@@ -246,15 +254,33 @@ class IDFlows(nn.Module):
             out.append(rans.encode_streams(z.reshape(-1)[:n], mean.reshape(-1)[:n], scale.reshape(-1)[:n], off))
         return out
 
+    def _pipes(self, dev, n_chunks: int, pipeline: int):
+        """Side CUDA streams for chunk-level pipelining, or [None] for in-line.
+        The streams are kept on the model: the caching allocator pools memory per stream, so fresh
+        streams on every call would turn every activation into a cudaMalloc."""
+        k = min(int(pipeline), n_chunks)
+        if k <= 1:
+            return [None]
+        cache = self.__dict__.setdefault("_side_streams", {})
+        have = cache.setdefault(dev.index, [])
+        while len(have) < k:
+            have.append(torch.cuda.Stream(dev))
+        return have[:k]
+
     def compress(self, images: torch.Tensor, cond: torch.Tensor | None = None, codec_batch: int | None = None,
-                 streams_per_segment: int = 1, check: bool = True, stats: list | None = None) -> CompressedBatch:
+                 streams_per_segment: int = 1, check: bool = True, stats: list | None = None,
+                 pipeline: int = 2) -> CompressedBatch:
         """Lossless compression of uint8 images (N, C, H, W) on the GPU.
 
         codec_batch: images per network pass (default: all of them).  It is recorded in the
         result because the decoder has to run the networks on batches of the same shape to get
         bit-identical prior outputs; the last chunk is padded with zero images whose streams are
         not stored.  streams_per_segment: rANS streams per (image, level); 0 selects the
-        reference's native partition (one stream per level per chunk, trainer.py:308-315)."""
+        reference's native partition (one stream per level per chunk, trainer.py:308-315).
+        pipeline: chunks in flight.  Chunks are independent, so chunk i runs on CUDA stream
+        i % pipeline: the coder kernels of one chunk (a few dozen serial streams, latency-bound,
+        a handful of warps) overlap the convolutions of the next one instead of idling the GPU
+        between them.  The bytes produced do not depend on it."""
         if images.dtype != torch.uint8 or images.dim() != 4:
             raise TypeError("images must be uint8 (N, C, H, W)")
         if tuple(images.shape[1:]) != (self.C, self.H, self.W):
@@ -266,25 +292,45 @@ class IDFlows(nn.Module):
         n = images.shape[0]
         cbs = int(codec_batch or max(n, 1))
         batch = CompressedBatch(n, (self.C, self.H, self.W), self.nsplit, cbs, int(streams_per_segment))
+        if cond is not None:
+            cond = cond.to(dev)
         with deterministic_convs(), torch.cuda.device(dev):
-            for i0 in range(0, n, cbs):
-                chunk = images[i0:i0 + cbs]
-                n_real = chunk.shape[0]
-                x = u8_to_grid(chunk)
-                c = None if cond is None else cond[i0:i0 + cbs].to(dev)
-                if n_real < cbs:
-                    x = torch.cat([x, x.new_zeros((cbs - n_real,) + tuple(x.shape[1:]))])
-                    if c is not None:
-                        c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
-                batch.sections.append(self._chunk_forward(x, c, n_real, int(streams_per_segment), stats))
+            main = torch.cuda.current_stream(dev)
+            pipes = self._pipes(dev, (n + cbs - 1) // cbs, pipeline)
+            for ci, i0 in enumerate(range(0, n, cbs)):
+                side = pipes[ci % len(pipes)]
+                if side is not None and ci < len(pipes):
+                    side.wait_stream(main)                      # inputs were produced on the main stream
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                    chunk = images[i0:i0 + cbs]
+                    n_real = chunk.shape[0]
+                    x = u8_to_grid(chunk)
+                    c = None if cond is None else cond[i0:i0 + cbs]
+                    if n_real < cbs:
+                        x = torch.cat([x, x.new_zeros((cbs - n_real,) + tuple(x.shape[1:]))])
+                        if c is not None:
+                            c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
+                    section = self._chunk_forward(x, c, n_real, int(streams_per_segment), stats)
+                    if side is not None:
+                        for e in section:
+                            e.record_stream(main)
+                    batch.sections.append(section)
+            for side in pipes:
+                if side is not None:
+                    main.wait_stream(side)
         if check:
             for ch in batch.sections:
                 for e in ch:
                     e.check()
         return batch
 
-    def decompress(self, batch, cond: torch.Tensor | None = None, check: bool = True) -> torch.Tensor:
-        """Inverse of compress: CompressedBatch (or its bytes) -> uint8 images (N, C, H, W)."""
+    def decompress(self, batch, cond: torch.Tensor | None = None, check: bool = True, pipeline: int = 2) -> torch.Tensor:
+        """Inverse of compress: CompressedBatch (or its bytes) -> uint8 images (N, C, H, W).
+
+        Inside a chunk the levels are a strict chain (prior convolutions -> rANS decode -> inverse
+        flow -> next level's prior), and the decode of a chunk is a few dozen serial streams; with
+        pipeline > 1 chunk i runs on CUDA stream i % pipeline, so that chain of one chunk overlaps
+        the convolutions of another (level-pipelined decompress)."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise _lib.FlicError("decompress needs the model on a CUDA device (no CPU fallback)")
@@ -294,35 +340,50 @@ class IDFlows(nn.Module):
             raise ValueError("container does not match this model")
         n, cbs, sps = batch.n_images, batch.codec_batch, batch.streams_per_segment
         outs, statuses = [], []
+        if cond is not None:
+            cond = cond.to(dev)
         with deterministic_convs(), torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            pipes = self._pipes(dev, (n + cbs - 1) // cbs if cbs else 0, pipeline)
             for ci, i0 in enumerate(range(0, n, cbs)):
-                n_real = min(cbs, n - i0)
-                c = None if cond is None else cond[i0:i0 + cbs].to(dev)
-                if c is not None and n_real < cbs:
-                    c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
-                conds = self._cond_pyramid(c)
-                x = None
-                for level in reversed(range(self.nsplit)):
-                    block = self.blocks[level]
-                    cz, h, w = self.latents_shape[level]
-                    if level == self.nsplit - 1:
-                        probe = torch.zeros((cbs, cz, h, w), dtype=torch.float32, device=dev)
-                        mean, logscale = block["prior"](self._prior_input(level, probe, conds[level]))
-                    else:
-                        mean, logscale = block["prior"](self._prior_input(level, x, conds[level]))
-                    mean, scale = mean.contiguous(), torch.exp(logscale.contiguous())
-                    nsym = n_real * cz * h * w
-                    off = self._segment_offsets(level, n_real, sps, dev)
-                    z = torch.zeros((cbs, cz, h, w), dtype=torch.float32, device=dev)
-                    _, _, st = rans.decode_streams(batch.sections[ci][level], mean.reshape(-1)[:nsym],
-                                                   scale.reshape(-1)[:nsym], off, out=z.view(-1)[:nsym])
-                    statuses.append(st)
-                    x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
-                    x = self._flow_backward(block, x)
-                    x = block["extend"].backward(x)
-                img, st8 = grid_to_u8(x[:n_real])
-                statuses.append(st8)
-                outs.append(img)
+                side = pipes[ci % len(pipes)]
+                if side is not None and ci < len(pipes):
+                    side.wait_stream(main)
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                    n_real = min(cbs, n - i0)
+                    c = None if cond is None else cond[i0:i0 + cbs]
+                    if c is not None and n_real < cbs:
+                        c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
+                    conds = self._cond_pyramid(c)
+                    x = None
+                    for level in reversed(range(self.nsplit)):
+                        block = self.blocks[level]
+                        cz, h, w = self.latents_shape[level]
+                        if level == self.nsplit - 1:
+                            probe = torch.zeros((cbs, cz, h, w), dtype=torch.float32, device=dev)
+                            mean, logscale = block["prior"](self._prior_input(level, probe, conds[level]))
+                        else:
+                            mean, logscale = block["prior"](self._prior_input(level, x, conds[level]))
+                        mean, scale = mean.contiguous(), torch.exp(logscale.contiguous())
+                        nsym = n_real * cz * h * w
+                        off = self._segment_offsets(level, n_real, sps, dev)
+                        z = torch.zeros((cbs, cz, h, w), dtype=torch.float32, device=dev)
+                        _, _, st = rans.decode_streams(batch.sections[ci][level], mean.reshape(-1)[:nsym],
+                                                       scale.reshape(-1)[:nsym], off, out=z.view(-1)[:nsym])
+                        statuses.append(st)
+                        x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
+                        x = self._flow_backward(block, x)
+                        x = block["extend"].backward(x)
+                    img, st8 = grid_to_u8(x[:n_real])
+                    statuses.append(st8)
+                    outs.append(img)
+                    if side is not None:
+                        for t in statuses[-(self.nsplit + 1):]:
+                            t.record_stream(main)
+                        img.record_stream(main)
+            for side in pipes:
+                if side is not None:
+                    main.wait_stream(side)
         if check:
             for st in statuses:
                 rans.check_status(st)

@@ -119,6 +119,12 @@ class EncodedStreams:
             _lib.raise_for_status(allbits)
         return self
 
+    def record_stream(self, stream) -> "EncodedStreams":
+        """The tensors were produced on a side CUDA stream and will be used on `stream`."""
+        for t in (self.words, self.word_offsets, self.final_states, self.status):
+            t.record_stream(stream)
+        return self
+
     def trimmed(self) -> "EncodedStreams":
         n = self.n_words()
         return EncodedStreams(self.words[:n].clone(), self.word_offsets, self.final_states, self.status, self.n_symbols)

@@ -125,6 +125,21 @@ int flic_permute_channels(const float* src, float* dst, const int32_t* perm, int
 int flic_squeeze(const float* src, float* dst, int64_t batch, int64_t C, int64_t H, int64_t W,
                  int scale, int direction, flic_cuda_stream_t stream);
 
+/* N4: the ideal code length, fused.
+ * DLogistic.log_prob (distlib.py:40-55) for x, mean, logscale of shape (batch, per_item), with
+ * the per-image sum of IDFlows.log_likelihood (flows.py:154-169) computed in the same pass:
+ *   logp_out  float32[batch * per_item], device, or NULL
+ *   sum_out   float32[batch], device, or NULL (natural-log units; the caller divides by H*W*C)
+ * Floating point (not part of the bitstream): same float operations as the torch formula. */
+int flic_dlogistic_log_prob(const float* x, const float* mean, const float* logscale, int64_t batch,
+                            int64_t per_item, int nbits, float eps, float* logp_out, float* sum_out,
+                            flic_cuda_stream_t stream);
+
+/* DLogistic.sample (distlib.py:57-70) from caller-supplied uniforms u in (0, 1):
+ * out = Round_nbits(log(u / (1 - u)) * exp(logscale) + mean). */
+int flic_dlogistic_sample(const float* u, const float* mean, const float* logscale, int64_t n, int nbits,
+                          float* out, flic_cuda_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host entry points (copies inside)
  * ------------------------------------------------------------------------------------------ */

@@ -430,3 +430,74 @@ def test_device_part1_exhaustive_over_every_float_argument(oracle):
                     bad += b_
                     firsts += first.tolist()
     assert bad == 0, [hex(f) for f in firsts[:16]]
+
+
+# ---- N4: fused DLogistic log-probability / sampler (floating point: tolerance, not bit equality) --
+
+@pytest.mark.parametrize("shape", [(7, 6, 16, 16), (3, 48, 4, 4), (1, 1, 1, 5)])
+def test_fused_dlogistic_log_prob_matches_torch_formula(shape):
+    """flic_dlogistic_log_prob against the reference's formula (distlib.py:40-55) evaluated by
+    torch in fp32 on the same device: elementwise within 1e-5 (abs + rel; the kernel runs the same
+    float operations, only the summation order of the reduction differs), per-image sums within
+    1e-5 relative (the kernel accumulates in double, torch.sum in float)."""
+    from flic_b200.distlib import DLogistic
+    g = torch.Generator(device="cuda").manual_seed(5)
+    mean = (torch.rand(shape, device="cuda", generator=g) - 0.5) * 2
+    logscale = (torch.rand(shape, device="cuda", generator=g) - 0.5) * 8 - 3
+    x = torch.round((mean + torch.exp(logscale) * torch.randn(shape, device="cuda", generator=g) * 2) * 256) / 256
+    x[0].view(-1)[0] = 7.0                       # far tail: log(eps) floor
+    dist = DLogistic()
+    want = DLogistic._log_prob_torch(x, mean, logscale, 8)
+    got = dist.log_prob(x, mean, logscale, 8)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    sums = dist.log_prob_sums(x, mean, logscale, 8)
+    want_sums = want.double().flatten(1).sum(1)
+    assert torch.allclose(sums.double(), want_sums, rtol=1e-5, atol=1e-4)
+    # autograd still goes through the torch formula
+    m2 = mean.clone().requires_grad_(True)
+    dist.log_prob(x, m2, logscale, 8).sum().backward()
+    assert m2.grad is not None and torch.isfinite(m2.grad).all()
+
+
+def test_fused_log_likelihood_matches_reference_golden():
+    """IDFlows.log_likelihood through the fused per-image reduction, fed the reference's own
+    latents / means / logscales (tests/golden/flow_tiny.npz, produced by the reference's model on
+    the CPU), against the log-likelihood the reference computed from them."""
+    g = np.load(GOLDEN)
+    model = build_tiny().cuda().eval()
+    lat = [torch.from_numpy(g[f"id.latent{i}"]).cuda() for i in range(model.nsplit)]
+    means = [torch.from_numpy(g[f"id.mean{i}"]).cuda() for i in range(model.nsplit)]
+    logs = [torch.from_numpy(g[f"id.logscale{i}"]).cuda() for i in range(model.nsplit)]
+    with torch.no_grad():
+        ll, per_level = model.log_likelihood(lat, means, logs)
+    assert np.allclose(ll.cpu().numpy(), g["id.logp"], rtol=2e-5, atol=2e-5)
+    assert len(per_level) == model.nsplit
+
+
+def test_fused_dlogistic_sample_matches_torch_formula():
+    from flic_b200.distlib import DLogistic
+    shape = (4, 6, 16, 16)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    mean = (torch.rand(shape, device="cuda", generator=g) - 0.5) * 2
+    logscale = (torch.rand(shape, device="cuda", generator=g) - 0.5) * 4 - 3
+    dist = DLogistic()
+    torch.manual_seed(123)
+    got = dist.sample(mean, logscale, 8)
+    torch.manual_seed(123)
+    u = torch.rand_like(mean)
+    want = dist.round(torch.log(u / (1 - u)) * torch.exp(logscale) + mean, nbits=8)
+    assert torch.equal(got * 256, torch.round(got * 256))                 # on the 1/256 grid
+    diff = (got - want).abs()
+    assert float(diff.max()) <= 1 / 256 and float((diff != 0).float().mean()) < 1e-4
+
+
+def test_chunk_pipelining_does_not_change_the_bytes():
+    """N3: chunks run on rotating CUDA streams (pipeline > 1).  The container must be byte-identical
+    to the in-line result and decode to the pixels whichever way either side was run."""
+    model = build_tiny().cuda().eval()
+    img = torch.randint(0, 256, (11, 3, 16, 16), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
+    blobs = [model.compress(img, codec_batch=3, pipeline=p).to_bytes() for p in (1, 2, 4)]
+    assert blobs[0] == blobs[1] == blobs[2]
+    for p in (1, 3):
+        assert torch.equal(model.decompress(blobs[0], pipeline=p), img)
