@@ -501,3 +501,88 @@ def test_chunk_pipelining_does_not_change_the_bytes():
     assert blobs[0] == blobs[1] == blobs[2]
     for p in (1, 3):
         assert torch.equal(model.decompress(blobs[0], pipeline=p), img)
+
+
+# ---- BASELINE.json configs[2] and configs[3]: the shapes and stream partitions of the patch-wise
+# ---- models (network width reduced; the coder sees the same symbol counts and stream counts) ----
+
+def _check_streams_against_oracle(oracle, model, batch, stats, n, sps):
+    cbs = batch.codec_batch
+    k = 0
+    for ci, chunk in enumerate(batch.sections):
+        n_real = min(cbs, n - ci * cbs)
+        for level, enc in enumerate(chunk):
+            z, mean, logscale = stats[k]
+            k += 1
+            nsym = n_real * int(np.prod(model.latents_shape[level]))
+            scale = torch.exp(logscale.contiguous())
+            off = model._segment_offsets(level, n_real, sps, "cpu").numpy()
+            words, woff, states, status = oracle.encode_streams(
+                z.reshape(-1)[:nsym].cpu().numpy(), mean.contiguous().reshape(-1)[:nsym].cpu().numpy(),
+                scale.reshape(-1)[:nsym].cpu().numpy(), off, n_threads=8)
+            assert not status.any()
+            assert np.array_equal(enc.word_offsets.cpu().numpy(), woff)
+            assert np.array_equal(enc.words.cpu().numpy().view(np.uint32)[:words.size], words)
+            assert np.array_equal(enc.final_states.cpu().numpy().view(np.uint64), states)
+
+
+def test_config_resflows_smallpatch_patchwise_coding(oracle):
+    """configs/resflows_smallpatch.yaml:3-43,73-75: IDFlows nsplit 1 on 8x8 patches (latent
+    (12,4,4) = 192 symbols), 27 x 23 = 621 patches per 216x184 image, batch 16 -> 9936 independent
+    rANS streams per batch.  Lossless, and every stream identical to the reference coder's."""
+    import random
+    from flic_b200 import flows
+    layer = dict(name="DenseLayer", act="ReLU")
+    cfg = dict(name="IDFlows", nflows=12, nbits=8, nsplit=1, H=8, W=8, C=3,
+               couple=dict(name="AdditiveCouple", split=0.75, round=dict(name="Round", nbits=8),
+                           nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=layer)),
+               extenddim=dict(name="ExtendDim", scale=2),
+               prior=dict(name="Prior", round=dict(name="Round", nbits=8),
+                          nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=layer)),
+               distribution=dict(name="DLogistic"), round=dict(name="Round", nbits=8))
+    torch.manual_seed(0)
+    random.seed(0)
+    model = flows.build_model(cfg)
+    flows.perturb_heads(model, 0.02)
+    model = model.cuda().eval()
+    assert model.latents_shape == [(12, 4, 4)]
+    images = torch.randint(0, 256, (16, 3, 216, 184), dtype=torch.uint8, generator=torch.Generator().manual_seed(8))
+    # Patching (trainer.py residual path): non-overlapping 8x8 tiles, row-major
+    patches = images.unfold(2, 8, 8).unfold(3, 8, 8).permute(0, 2, 3, 1, 4, 5).reshape(-1, 3, 8, 8).contiguous().cuda()
+    assert patches.shape[0] == 16 * 621
+    stats = []
+    batch = model.compress(patches, stats=stats)
+    assert batch.n_streams() == 9936
+    _check_streams_against_oracle(oracle, model, batch, stats, patches.shape[0], 1)
+    assert torch.equal(model.decompress(batch.to_bytes()), patches)
+
+
+def test_config_vqvae_conditional_patches(oracle):
+    """configs/resflow-patches-vqvae.yaml:3-44: ConditionalFlows on 27x23 patches, ExtendDim scale 1,
+    nsplit 1 (latent (3,27,23) = 1863 symbols, an odd stream length), 64 patches per image, the prior
+    conditioned on a (here random) reconstruction (flows.py:303-327)."""
+    import random
+    from flic_b200 import flows
+    layer = dict(name="DenseLayer", act="LeakyReLU")
+    cfg = dict(name="ConditionalFlows", nflows=8, nbits=8, nsplit=1, H=27, W=23, C=3, conv_for_cond=False,
+               couple=dict(name="AdditiveCouple", split=0.75, round=dict(name="Round", nbits=8),
+                           nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=layer)),
+               extenddim=dict(name="ExtendDim", scale=1),
+               prior=dict(name="Prior", round=dict(name="Round", nbits=8),
+                          nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=layer)),
+               distribution=dict(name="DLogistic"), round=dict(name="Round", nbits=8))
+    torch.manual_seed(0)
+    random.seed(0)
+    model = flows.build_model(cfg)
+    flows.perturb_heads(model, 0.02)
+    model = model.cuda().eval()
+    assert model.latents_shape == [(3, 27, 23)]
+    g = torch.Generator().manual_seed(4)
+    n = 2 * 64
+    patches = torch.randint(0, 256, (n, 3, 27, 23), dtype=torch.uint8, generator=g).cuda()
+    cond = flows.u8_to_grid(torch.randint(0, 256, (n, 3, 27, 23), dtype=torch.uint8, generator=g).cuda())
+    stats = []
+    batch = model.compress(patches, cond=cond, codec_batch=48, stats=stats)      # 48 does not divide 128: padded last chunk
+    assert batch.n_streams() == n
+    _check_streams_against_oracle(oracle, model, batch, stats, n, 1)
+    assert torch.equal(model.decompress(batch.to_bytes(), cond=cond), patches)
