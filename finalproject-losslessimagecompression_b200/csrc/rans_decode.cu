@@ -146,6 +146,138 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
     }
 }
 
+// ---- fast path: every lane stages its own stream ----------------------------------------------
+// The kernel above moves (mean, scale) tiles with warp-wide copies, which costs four 64-bit
+// shuffles and two address computations per 32 elements each way -- about 40 of its ~250
+// instructions per symbol.  Here each lane copies 32-byte blocks of ITS OWN stream: two 16-byte
+// cp.async per array per 8 symbols, and the 8 decoded symbols leave as two 16-byte stores.
+// A 32-byte block is one DRAM sector, so the traffic is still exactly the algorithmic bytes.
+//
+// Blocks are cut on the 32-byte grid of the arrays' addresses: with shift = (address / 4) mod 8,
+// block T of a lane holds the symbols i with (i + shift) >> 3 == T.  The launcher uses this kernel
+// only when mean, scale and x_out share the same shift (true whenever they are allocations of
+// their own, or equal slices of such).  A stream's first and last block may be partial; those
+// go element by element.
+constexpr int kBlk = 8;           // symbols per lane per block (32 bytes)
+constexpr int kBlkPitch = 12;     // floats per lane row in shared memory: 48 B keeps the 16-byte
+                                  // accesses of a quarter-warp on disjoint banks
+
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? FLIC_DEC_MIN_BLOCKS : 16)
+rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ word_offsets,
+                        const uint64_t* __restrict__ states, const float* __restrict__ mean,
+                        const float* __restrict__ scale, const int64_t* __restrict__ offsets,
+                        int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
+                        int32_t* __restrict__ status, int check_end, int shift) {
+    __shared__ uint64_t s_tab[32];
+    __shared__ __align__(16) float s_mean[WARPS][2][kLanes][kBlkPitch];
+    __shared__ __align__(16) float s_scale[WARPS][2][kLanes][kBlkPitch];
+    stage_exp_table(s_tab);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t first = ((int64_t)blockIdx.x * WARPS + warp) * kLanes;
+    if (first >= n_streams) return;
+    const int64_t stream = first + lane;
+    const bool live = stream < n_streams;
+
+    const int64_t beg = live ? offsets[stream] : 0;
+    int64_t len = live ? offsets[stream + 1] - beg : 0;
+    const int64_t wbeg = live ? word_offsets[stream] : 0;
+    const int64_t wcount = live ? word_offsets[stream + 1] - wbeg : 0;
+    const bool too_long = wcount > 0xffffffffll;
+    if (too_long) len = 0;
+    const int64_t end = beg + len;
+    // blocks of this lane, last to first: T_hi, T_hi - 1, ..., T_lo
+    const int64_t t_hi = (end - 1 + shift) >> 3, t_lo = (beg + shift) >> 3;
+    const int64_t my_blocks = len > 0 ? t_hi - t_lo + 1 : 0;
+    const int64_t n_iter = warp_max_i64(my_blocks);
+
+    const uint32_t* wp = packed + wbeg;
+    uint32_t wrem = too_long ? 0u : (uint32_t)wcount;
+    uint64_t state = live ? states[stream] : kRansL;
+    uint32_t next_word = wrem ? __ldg(wp + (wrem - 1)) : 0u;
+    int32_t flags = too_long ? ST_TOO_LONG : 0;
+
+    // this lane's rows in the two buffers
+    float* const row_mean = s_mean[warp][0][lane];
+    float* const row_scale = s_scale[warp][0][lane];
+    constexpr int kBufStride = kLanes * kBlkPitch;
+
+    // stage block number q (counted from the stream's end) into buffer q & 1
+    auto prefetch = [&](int64_t q) {
+        if (q < my_blocks) {
+            const int64_t i0 = ((t_hi - q) << 3) - shift;       // first symbol index of the block
+            float* dm = row_mean + (int)(q & 1) * kBufStride;
+            float* ds = row_scale + (int)(q & 1) * kBufStride;
+            if (i0 >= beg && i0 + kBlk <= end) {                // whole block inside the stream
+                cp_async_16(dm, mean + i0);
+                cp_async_16(dm + 4, mean + i0 + 4);
+                cp_async_16(ds, scale + i0);
+                cp_async_16(ds + 4, scale + i0 + 4);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kBlk; ++j)
+                    if (i0 + j >= beg && i0 + j < end) {
+                        cp_async_f32(dm + j, mean + i0 + j);
+                        cp_async_f32(ds + j, scale + i0 + j);
+                    }
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (n_iter > 0) prefetch(0);
+    for (int64_t q = 0; q < n_iter; ++q) {
+        if (q + 1 < n_iter) {
+            prefetch(q + 1);
+            cp_async_wait<1>();   // block q has landed; block q+1 may still be in flight
+        } else {
+            cp_async_wait<0>();
+        }
+        // each lane reads only what it copied itself: no warp barrier needed
+        if (q < my_blocks) {
+            const int64_t i0 = ((t_hi - q) << 3) - shift;
+            float* bm = row_mean + (int)(q & 1) * kBufStride;
+            const float* bs = row_scale + (int)(q & 1) * kBufStride;
+            const int j_lo = i0 >= beg ? 0 : (int)(beg - i0);
+            const int j_hi = i0 + kBlk <= end ? kBlk : (int)(end - i0);
+#pragma unroll 1
+            for (int j = j_hi - 1; j >= j_lo; --j) {
+                if (state < kRansL) {  // rans.pyx:87-89
+                    if (wrem) {
+                        state = (state << 32) | next_word;
+                        --wrem;
+                        if (wrem) next_word = __ldg(wp + (wrem - 1));
+                    } else {
+                        flags |= ST_UNDERRUN;
+                    }
+                }
+                const int s = decode_symbol(state, bm[j], bs[j], s_tab, flags);
+                bm[j] = (float)s * 0.00390625f;  // s / 256., exact; the mean slot is free now
+            }
+            if (j_lo == 0 && j_hi == kBlk) {
+                const float4 a = *reinterpret_cast<const float4*>(bm);
+                const float4 b = *reinterpret_cast<const float4*>(bm + 4);
+                *reinterpret_cast<float4*>(x_out + i0) = a;
+                *reinterpret_cast<float4*>(x_out + i0 + 4) = b;
+            } else {
+                for (int j = j_lo; j < j_hi; ++j) x_out[i0 + j] = bm[j];
+            }
+        }
+    }
+    if (live) {
+        if (check_end && !too_long && (state != kRansL || wrem != 0)) flags |= ST_BAD_END_STATE;
+        end_states[stream] = state;
+        status[stream] = flags;
+    }
+}
+
 cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offsets,
                                const uint64_t* states, const float* mean, const float* scale,
                                const int64_t* offsets, int64_t n_streams, float* x_out,
@@ -153,11 +285,24 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
                                cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
     const int64_t warps = (n_streams + kLanes - 1) / kLanes;
-    if (warps <= (int64_t)sm_count() * 16) {
+    const bool small = warps <= (int64_t)sm_count() * 16;
+    const int64_t blocks = (warps + kCoderWarps - 1) / kCoderWarps;
+    // the lane-staged kernel needs the three symbol arrays on the same 32-byte phase
+    const int sh_m = (int)(((uintptr_t)mean >> 2) & 7), sh_s = (int)(((uintptr_t)scale >> 2) & 7);
+    const int sh_x = (int)(((uintptr_t)x_out >> 2) & 7);
+    const bool lane_staged = sh_m == sh_s && sh_m == sh_x && ((uintptr_t)mean & 3) == 0 &&
+                             ((uintptr_t)scale & 3) == 0 && ((uintptr_t)x_out & 3) == 0;
+    if (lane_staged) {
+        if (small)
+            rans_decode_lane_kernel<1><<<(unsigned)warps, 32, 0, stream>>>(
+                packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, sh_m);
+        else
+            rans_decode_lane_kernel<kCoderWarps><<<(unsigned)blocks, kCoderWarps * 32, 0, stream>>>(
+                packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, sh_m);
+    } else if (small) {
         rans_decode_kernel<1><<<(unsigned)warps, 32, 0, stream>>>(
             packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end);
     } else {
-        const int64_t blocks = (warps + kCoderWarps - 1) / kCoderWarps;
         rans_decode_kernel<kCoderWarps><<<(unsigned)blocks, kCoderWarps * 32, 0, stream>>>(
             packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end);
     }

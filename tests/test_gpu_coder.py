@@ -199,3 +199,26 @@ def test_full_size_round_trip_properties():
     assert bool((end == (1 << 32)).all().item())
     bps = enc.bits() / n
     assert 4.2 < bps < 4.7  # rans/test.py distribution codes at ~4.4 bits/symbol
+
+
+@pytest.mark.parametrize("pads", [(0, 0, 0), (3, 3, 3), (5, 5, 5), (1, 2, 3), (0, 4, 0)])
+def test_decode_on_any_array_alignment(oracle, pads):
+    """The decoder stages 32-byte blocks per lane when mean, scale and the output share the same
+    32-byte phase (any phase), and falls back to warp-wide 4-byte staging when they do not.  Both
+    must return the symbols for ragged partitions whose streams start anywhere."""
+    from flic_b200 import rans
+    n, ns = 150_000, 333
+    x, mean, scale = gen("test", n, 77)
+    off = ragged_offsets(n, ns, 13)
+    xd, md, sd = _cuda(x, mean, scale)
+    offd = torch.from_numpy(off).cuda()
+    enc = rans.encode_streams(xd, md, sd, offd)
+    pm, ps, px = pads
+    mbuf = torch.zeros(n + 8, device="cuda"); mbuf[pm:pm + n] = md
+    sbuf = torch.ones(n + 8, device="cuda"); sbuf[ps:ps + n] = sd
+    obuf = torch.full((n + 8,), -7.0, device="cuda")
+    xr, end_states, status = rans.decode_streams(enc, mbuf[pm:pm + n], sbuf[ps:ps + n], offd, out=obuf[px:px + n])
+    assert not status.any().item()
+    assert torch.equal(obuf[px:px + n], xd)
+    assert bool((obuf[:px] == -7.0).all().item()) and bool((obuf[px + n:] == -7.0).all().item())   # nothing outside
+    assert bool((end_states == (1 << 32)).all().item())
