@@ -158,9 +158,14 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
 // only when mean, scale and x_out share the same shift (true whenever they are allocations of
 // their own, or equal slices of such).  A stream's first and last block may be partial; those
 // go element by element.
-constexpr int kBlk = 8;           // symbols per lane per block (32 bytes)
-constexpr int kBlkPitch = 12;     // floats per lane row in shared memory: 48 B keeps the 16-byte
-                                  // accesses of a quarter-warp on disjoint banks
+#ifndef FLIC_LANE_BLOCK
+#define FLIC_LANE_BLOCK 8
+#endif
+constexpr int kBlk = FLIC_LANE_BLOCK;   // symbols per lane per block: 8 (one 32-byte sector) or 4
+constexpr int kBlkShift = kBlk == 8 ? 3 : 2;           // symbols per lane per block (32 bytes)
+// floats per lane row in shared memory: 8-symbol rows are padded to 48 B so that the 16-byte
+// accesses of a quarter-warp fall on disjoint banks; 4-symbol rows (16 B) are conflict-free as is
+constexpr int kBlkPitch = kBlk == 8 ? 12 : 4;
 
 __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -194,7 +199,7 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     if (too_long) len = 0;
     const int64_t end = beg + len;
     // blocks of this lane, last to first: T_hi, T_hi - 1, ..., T_lo
-    const int64_t t_hi = (end - 1 + shift) >> 3, t_lo = (beg + shift) >> 3;
+    const int64_t t_hi = (end - 1 + shift) >> kBlkShift, t_lo = (beg + shift) >> kBlkShift;
     const int64_t my_blocks = len > 0 ? t_hi - t_lo + 1 : 0;
     const int64_t n_iter = warp_max_i64(my_blocks);
 
@@ -212,14 +217,16 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     // stage block number q (counted from the stream's end) into buffer q & 1
     auto prefetch = [&](int64_t q) {
         if (q < my_blocks) {
-            const int64_t i0 = ((t_hi - q) << 3) - shift;       // first symbol index of the block
+            const int64_t i0 = ((t_hi - q) << kBlkShift) - shift;       // first symbol index of the block
             float* dm = row_mean + (int)(q & 1) * kBufStride;
             float* ds = row_scale + (int)(q & 1) * kBufStride;
             if (i0 >= beg && i0 + kBlk <= end) {                // whole block inside the stream
                 cp_async_16(dm, mean + i0);
-                cp_async_16(dm + 4, mean + i0 + 4);
                 cp_async_16(ds, scale + i0);
-                cp_async_16(ds + 4, scale + i0 + 4);
+                if (kBlk == 8) {
+                    cp_async_16(dm + 4, mean + i0 + 4);
+                    cp_async_16(ds + 4, scale + i0 + 4);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < kBlk; ++j)
@@ -242,7 +249,7 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         }
         // each lane reads only what it copied itself: no warp barrier needed
         if (q < my_blocks) {
-            const int64_t i0 = ((t_hi - q) << 3) - shift;
+            const int64_t i0 = ((t_hi - q) << kBlkShift) - shift;
             float* bm = row_mean + (int)(q & 1) * kBufStride;
             const float* bs = row_scale + (int)(q & 1) * kBufStride;
             const int j_lo = i0 >= beg ? 0 : (int)(beg - i0);
@@ -262,10 +269,8 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                 bm[j] = (float)s * 0.00390625f;  // s / 256., exact; the mean slot is free now
             }
             if (j_lo == 0 && j_hi == kBlk) {
-                const float4 a = *reinterpret_cast<const float4*>(bm);
-                const float4 b = *reinterpret_cast<const float4*>(bm + 4);
-                *reinterpret_cast<float4*>(x_out + i0) = a;
-                *reinterpret_cast<float4*>(x_out + i0 + 4) = b;
+                *reinterpret_cast<float4*>(x_out + i0) = *reinterpret_cast<const float4*>(bm);
+                if (kBlk == 8) *reinterpret_cast<float4*>(x_out + i0 + 4) = *reinterpret_cast<const float4*>(bm + 4);
             } else {
                 for (int j = j_lo; j < j_hi; ++j) x_out[i0 + j] = bm[j];
             }
@@ -288,8 +293,8 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
     const bool small = warps <= (int64_t)sm_count() * 16;
     const int64_t blocks = (warps + kCoderWarps - 1) / kCoderWarps;
     // the lane-staged kernel needs the three symbol arrays on the same 32-byte phase
-    const int sh_m = (int)(((uintptr_t)mean >> 2) & 7), sh_s = (int)(((uintptr_t)scale >> 2) & 7);
-    const int sh_x = (int)(((uintptr_t)x_out >> 2) & 7);
+    const int sh_m = (int)(((uintptr_t)mean >> 2) & (kBlk - 1)), sh_s = (int)(((uintptr_t)scale >> 2) & (kBlk - 1));
+    const int sh_x = (int)(((uintptr_t)x_out >> 2) & (kBlk - 1));
     const bool lane_staged = sh_m == sh_s && sh_m == sh_x && ((uintptr_t)mean & 3) == 0 &&
                              ((uintptr_t)scale & 3) == 0 && ((uintptr_t)x_out & 3) == 0;
     if (lane_staged) {
