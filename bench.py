@@ -319,13 +319,16 @@ def run_flic(args) -> dict | None:
 
     peaks = read_peaks()
     alg_bytes = 12.0 + bits_per_symbol / 8.0                      # per symbol, each direction
-    dom_name, dom_ms = ("rans_decode_kernel", dec_ms) if dec_ms >= enc_ms else ("rans_encode_kernel (+scan, pack)", enc_ms)
+    enc_kernel = _lib.lib().flic_last_coder_kernel(0).decode() or "rans_encode_kernel"
+    dec_kernel = _lib.lib().flic_last_coder_kernel(1).decode() or "rans_decode_kernel"
+    dom_name, dom_ms = (dec_kernel, dec_ms) if dec_ms >= enc_ms else (enc_kernel + " (+scan, pack)", enc_ms)
     achieved = n * alg_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 5), "peak_source": peaks["source"],
                 "algorithmic_bytes_per_symbol": round(alg_bytes, 4), "symbols_per_launch": n,
                 "avg_launch_ms": round(dom_ms, 4), "traffic": read_traffic(dom_name, n),
                 "encode_ms": round(enc_ms, 4), "decode_ms": round(dec_ms, 4),
+                "encode_kernel": enc_kernel, "decode_kernel": dec_kernel,
                 "encode_GBps_algorithmic": round(n * alg_bytes / (enc_ms * 1e-3) / 1e9, 2),
                 "decode_GBps_algorithmic": round(n * alg_bytes / (dec_ms * 1e-3) / 1e9, 2)}
     line = {
@@ -485,9 +488,9 @@ def read_traffic(kernel: str, n_symbols: int):
     capture (profiles/traffic.json), scaled per symbol to this launch; None when not captured."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        for key, rec in t.items():
-            if kernel.startswith(key):
-                return round(rec["dram_bytes_per_symbol"] * n_symbols)
+        name = kernel.split(" ")[0]
+        if name in t:
+            return round(t[name]["dram_bytes_per_symbol"] * n_symbols)
     except Exception:
         pass
     return None
@@ -511,7 +514,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="flic", choices=["flic", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "full"])
-    ap.add_argument("--images", type=int, default=65536, help="images per step per GPU (sweep)")
+    ap.add_argument("--images", type=int, default=131072, help="images per step per GPU (sweep)")
     ap.add_argument("--e2e-images", type=int, default=8192)
     ap.add_argument("--batch", type=int, default=256, help="images per step per GPU (full)")
     ap.add_argument("--codec-batch", type=int, default=64)

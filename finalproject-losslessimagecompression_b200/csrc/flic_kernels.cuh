@@ -12,6 +12,10 @@ constexpr int kLanes = 32;
 constexpr int kTile = 32;
 constexpr int kCoderWarps = 4;  // warps per CTA in encode/decode kernels
 
+// Name of the coder kernel the last launch_rans_encode (which = 0) / launch_rans_decode (1) chose.
+const char* last_coder_kernel(int which);
+void note_coder_kernel(int which, const char* name);
+
 // K1  (x, mean, scale) -> (start, freq)                     rans/rans.pyx:49-56
 cudaError_t launch_cdf_tables(const float* x, const float* mean, const float* scale, int64_t n,
                               uint32_t* start, uint32_t* freq, int32_t* status_word,

@@ -297,6 +297,7 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
     const int sh_x = (int)(((uintptr_t)x_out >> 2) & (kBlk - 1));
     const bool lane_staged = sh_m == sh_s && sh_m == sh_x && ((uintptr_t)mean & 3) == 0 &&
                              ((uintptr_t)scale & 3) == 0 && ((uintptr_t)x_out & 3) == 0;
+    note_coder_kernel(1, lane_staged ? "rans_decode_lane_kernel" : "rans_decode_kernel");
     if (lane_staged) {
         if (small)
             rans_decode_lane_kernel<1><<<(unsigned)warps, 32, 0, stream>>>(

@@ -26,6 +26,10 @@
 
 namespace flic {
 
+static const char* g_last_kernel[2] = {"", ""};
+const char* last_coder_kernel(int which) { return g_last_kernel[which & 1]; }
+void note_coder_kernel(int which, const char* name) { g_last_kernel[which & 1] = name; }
+
 // Rows a producer warp loads (and then evaluates) back to back.
 constexpr int kRowBatch = 4;
 
@@ -263,12 +267,16 @@ cudaError_t launch_rans_encode(const float* x, const float* mean, const float* s
         const int64_t ctas = (blocks + kCoderWarps - 1) / kCoderWarps;
         rans_encode_lane_kernel<kCoderWarps><<<(unsigned)ctas, kCoderWarps * 32, 0, stream>>>(
             x, mean, scale, offsets, n_streams, init_states, scratch, counts, states, status, sh_x);
-    } else if (blocks >= (int64_t)sm_count() * 6)
+        note_coder_kernel(0, "rans_encode_lane_kernel");
+    } else if (blocks >= (int64_t)sm_count() * 6) {
         rans_encode_kernel<4><<<(unsigned)blocks, 5 * 32, 0, stream>>>(
             x, mean, scale, offsets, n_streams, init_states, scratch, counts, states, status);
-    else
+        note_coder_kernel(0, "rans_encode_kernel");
+    } else {
         rans_encode_kernel<8><<<(unsigned)blocks, 9 * 32, 0, stream>>>(
             x, mean, scale, offsets, n_streams, init_states, scratch, counts, states, status);
+        note_coder_kernel(0, "rans_encode_kernel");
+    }
     return cudaGetLastError();
 }
 

@@ -56,6 +56,9 @@ int flic_abi_version(void);
 const char* flic_last_error(void);
 /* Number of kernels launched by this library in the calling process since load (bench evidence). */
 int64_t flic_kernel_launches(void);
+/* Name of the kernel the most recent flic_rans_encode (which = 0) / flic_rans_decode (which = 1)
+ * launched: the coder has a lane-per-stream and a warp-cooperative variant of each (profiling aid). */
+const char* flic_last_coder_kernel(int which);
 
 /* ------------------------------------------------------------------------------------------
  * Device entry points
