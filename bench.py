@@ -304,6 +304,9 @@ def run_flic(args) -> dict | None:
     sharding.barrier(dev)
     clocks = sampler.stop()
     launches = _lib.kernel_launches() - launches0
+    # which variant of each coder kernel the timed launches used (chosen by stream count / alignment)
+    enc_kernel = _lib.lib().flic_last_coder_kernel(0).decode() or "rans_encode_kernel"
+    dec_kernel = _lib.lib().flic_last_coder_kernel(1).decode() or "rans_decode_kernel"
     ms_total = sharding.max_over_ranks(t0.elapsed_time(t1), dev)
     enc_ms = sum(a.elapsed_time(b) for a, b, _, _ in timers) / len(timers)
     dec_ms = sum(c.elapsed_time(d) for _, _, c, d in timers) / len(timers)
@@ -319,8 +322,6 @@ def run_flic(args) -> dict | None:
 
     peaks = read_peaks()
     alg_bytes = 12.0 + bits_per_symbol / 8.0                      # per symbol, each direction
-    enc_kernel = _lib.lib().flic_last_coder_kernel(0).decode() or "rans_encode_kernel"
-    dec_kernel = _lib.lib().flic_last_coder_kernel(1).decode() or "rans_decode_kernel"
     dom_name, dom_ms = (dec_kernel, dec_ms) if dec_ms >= enc_ms else (enc_kernel + " (+scan, pack)", enc_ms)
     achieved = n * alg_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"],
