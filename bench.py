@@ -340,6 +340,19 @@ def run_flic(args) -> dict | None:
     e2e = run_e2e(args, dev, rank, world)
 
     totals = sharding.gather_totals([n_words * 4 + 8 * ns, n], dev)
+
+    # ---- BASELINE.json configs[1] beside it: the whole model (PyTorch fp32 convolutions + this coder)
+    full = None
+    if not args.no_full:
+        del x, mean, scale, out, xr, xr_i, enc, enc_i, ws
+        torch.cuda.empty_cache()
+        try:
+            f = run_full(args, rank, world, dev, steps=3, warmup=3)
+            if f is not None:
+                full = {k: f[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config",
+                                          "bits_per_dim_container", "e2e", "gpu_launches", "dtype")}
+        except Exception as e:  # the sweep numbers stand on their own; say why this part is absent
+            full = {"value": None, "error": repr(e)[:200]}
     if rank != 0:
         return None
 
@@ -364,6 +377,7 @@ def run_flic(args) -> dict | None:
         "gpu_launches": int(launches), "clocks": clocks,
         "compressed_bytes_all_ranks": int(sum(t[0] for t in totals)),
         "partition_one_stream_per_image": per_image,
+        "full_model_configs1": full,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_subprocess(args)
@@ -427,7 +441,7 @@ def run_e2e(args, dev, rank, world) -> dict:
             "api": "flic_codec_encode + flic_codec_decode (include/flic_b200.h), pinned host buffers"}
 
 
-def run_full(args, rank, world, dev) -> dict | None:
+def run_full(args, rank, world, dev, steps=None, warmup=None) -> dict | None:
     """BASELINE.json configs[1]: imagenet64.yaml model, batch 256, full compress + decompress."""
     import random
 
@@ -457,9 +471,11 @@ def run_full(args, rank, world, dev) -> dict | None:
         blob = model.compress(himg.to(dev, non_blocking=True), codec_batch=args.codec_batch, check=False).to_bytes()
         return model.decompress(blob, check=False).cpu(), len(blob)
 
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     rec = step_device()
     assert torch.equal(rec, img), "full-path round trip is not lossless"
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(max(0, warmup - 1)):
         step_device()
     launches0 = _lib.kernel_launches()
     sampler = ClockSampler(dev.index)
@@ -468,15 +484,15 @@ def run_full(args, rank, world, dev) -> dict | None:
     sampler.start()
     t0, t1 = cuda_events()
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     t1.record()
     torch.cuda.synchronize()
     sharding.barrier(dev)
     clocks = sampler.stop()
     launches = _lib.kernel_launches() - launches0
-    ms_step = sharding.max_over_ranks(t0.elapsed_time(t1), dev) / args.steps
-    k = max(1, min(args.steps, 3))
+    ms_step = sharding.max_over_ranks(t0.elapsed_time(t1), dev) / steps
+    k = max(1, min(steps, 3))
     torch.cuda.synchronize()
     h0 = time.perf_counter()
     for _ in range(k):
@@ -488,7 +504,7 @@ def run_full(args, rank, world, dev) -> dict | None:
         return None
     raw = B * 3 * 64 * 64
     return {"metric": METRIC, "value": round(world * raw / (ms_step * 1e-3) / 1e6, 3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32 conv + f64/u64 coder", "data": "synthetic",
             "config": {"workload": "configs[1] imagenet64.yaml model (random init, heads N(0,0.02)), batch "
                                    f"{B} uniform-random uint8 3x64x64, IDFlows.compress + decompress",
@@ -548,6 +564,7 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-images-per-proc", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the configs[1] whole-model leg of the sweep line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "flic" else max(args.warmup, 1)
 
