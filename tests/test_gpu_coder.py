@@ -222,3 +222,38 @@ def test_decode_on_any_array_alignment(oracle, pads):
     assert torch.equal(obuf[px:px + n], xd)
     assert bool((obuf[:px] == -7.0).all().item()) and bool((obuf[px + n:] == -7.0).all().item())   # nothing outside
     assert bool((end_states == (1 << 32)).all().item())
+
+
+@pytest.mark.parametrize("pads", [(0, 0, 0), (5, 5, 5), (1, 2, 3)])
+def test_lane_per_stream_encoder_is_bit_exact(oracle, pads):
+    """From 24 warps of streams per SM (113 664 streams on a 148-SM B200) the encoder runs one lane
+    per stream, each lane staging 32-byte blocks of its own stream.  130 000 ragged streams (many
+    shorter than a block, some empty) on arrays at phase 0, at a common odd phase, and at different
+    phases (which falls back to the warp-cooperative kernel): every stream's (state, words) must be
+    the reference coder's, and the decoder must return the symbols."""
+    from flic_b200 import rans, _lib
+    n, n_streams = 2_400_000, 130_000
+    x, mean, scale = gen("test", n, 91)
+    off = ragged_offsets(n, n_streams, 92)
+    words_o, woff_o, states_o, _ = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+    bufs = []
+    for arr, pad, fill in ((x, pads[0], 0.0), (mean, pads[1], 0.0), (scale, pads[2], 1.0)):
+        b = torch.full((n + 8,), fill, device="cuda")
+        b[pad:pad + n] = torch.from_numpy(arr).cuda()
+        bufs.append(b[pad:pad + n])
+    xd, md, sd = bufs
+    offd = torch.from_numpy(off).cuda()
+    enc = rans.encode_streams(xd, md, sd, offd)
+    kernel = _lib.lib().flic_last_coder_kernel(0).decode()
+    same_phase = len(set(pads)) == 1
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    if same_phase and (n_streams + 31) // 32 >= 24 * sms:
+        assert kernel == "rans_encode_lane_kernel"
+    if not same_phase:
+        assert kernel == "rans_encode_kernel"
+    assert not enc.status.any().item()
+    assert np.array_equal(enc.word_offsets.cpu().numpy(), woff_o)
+    assert np.array_equal(_u64(enc.final_states), states_o)
+    assert np.array_equal(_u32(enc.words)[:words_o.size], words_o)
+    xr, end, status = rans.decode_streams(enc, md, sd, offd)
+    assert torch.equal(xr, xd) and not status.any().item() and bool((end == (1 << 32)).all().item())
