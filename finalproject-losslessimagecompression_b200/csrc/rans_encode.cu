@@ -241,12 +241,32 @@ rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ m
             const float* b = row + (int)(q & 1) * kBuf;
             const int j_lo = i0 >= beg ? 0 : (int)(beg - i0);
             const int j_hi = i0 + kBlk <= end ? kBlk : (int)(end - i0);
-#pragma unroll 2
-            for (int j = j_lo; j < j_hi; ++j) {
-                const int c = j ^ swz;
-                const SymbolTable e = make_table(b[c], b[kArr + c], b[2 * kArr + c], s_tab, flags);
-                uint32_t word;
-                if (rans_push(state, e.start, e.freq, word)) scratch[wpos++] = word;
+            if (kBlk == 8 && j_lo == 0 && j_hi == kBlk) {
+                // whole block: the row comes out of shared memory as 16-byte vectors (conflict-free
+                // by the swizzle) and the four symbols of each half are coded from registers
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int c = (4 * h) ^ swz;
+                    const float4 xv = *reinterpret_cast<const float4*>(b + c);
+                    const float4 mv = *reinterpret_cast<const float4*>(b + kArr + c);
+                    const float4 sv = *reinterpret_cast<const float4*>(b + 2 * kArr + c);
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const float ms[4] = {mv.x, mv.y, mv.z, mv.w};
+                    const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const SymbolTable e = make_table(xs[k], ms[k], ss[k], s_tab, flags);
+                        uint32_t word;
+                        if (rans_push(state, e.start, e.freq, word)) scratch[wpos++] = word;
+                    }
+                }
+            } else {
+                for (int j = j_lo; j < j_hi; ++j) {
+                    const int c = j ^ swz;
+                    const SymbolTable e = make_table(b[c], b[kArr + c], b[2 * kArr + c], s_tab, flags);
+                    uint32_t word;
+                    if (rans_push(state, e.start, e.freq, word)) scratch[wpos++] = word;
+                }
             }
         }
     }
