@@ -41,7 +41,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 #ifndef FLIC_DEC_MIN_BLOCKS
-#define FLIC_DEC_MIN_BLOCKS 8
+#define FLIC_DEC_MIN_BLOCKS 7
 #endif
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? FLIC_DEC_MIN_BLOCKS : 16)
@@ -254,9 +254,8 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
             const float* bs = row_scale + (int)(q & 1) * kBufStride;
             const int j_lo = i0 >= beg ? 0 : (int)(beg - i0);
             const int j_hi = i0 + kBlk <= end ? kBlk : (int)(end - i0);
-#pragma unroll 1
-            for (int j = j_hi - 1; j >= j_lo; --j) {
-                if (state < kRansL) {  // rans.pyx:87-89
+            auto pull = [&]() {  // rans.pyx:87-89
+                if (state < kRansL) {
                     if (wrem) {
                         state = (state << 32) | next_word;
                         --wrem;
@@ -265,14 +264,30 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                         flags |= ST_UNDERRUN;
                     }
                 }
-                const int s = decode_symbol(state, bm[j], bs[j], s_tab, flags);
-                bm[j] = (float)s * 0.00390625f;  // s / 256., exact; the mean slot is free now
-            }
-            if (j_lo == 0 && j_hi == kBlk) {
-                *reinterpret_cast<float4*>(x_out + i0) = *reinterpret_cast<const float4*>(bm);
-                if (kBlk == 8) *reinterpret_cast<float4*>(x_out + i0 + 4) = *reinterpret_cast<const float4*>(bm + 4);
+            };
+            if (kBlk == 8 && j_lo == 0 && j_hi == kBlk) {
+                // whole block: parameters come out of shared memory as 16-byte vectors (the row
+                // pitch keeps those conflict-free), four symbols are decoded from registers, last
+                // first, and leave as one 16-byte store
+#pragma unroll 1
+                for (int h = 1; h >= 0; --h) {
+                    const float4 mv = *reinterpret_cast<const float4*>(bm + 4 * h);
+                    const float4 sv = *reinterpret_cast<const float4*>(bs + 4 * h);
+                    const float ms[4] = {mv.x, mv.y, mv.z, mv.w};
+                    const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
+                    float xo[4];
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) {
+                        pull();
+                        xo[k] = (float)decode_symbol(state, ms[k], ss[k], s_tab, flags) * 0.00390625f;  // s / 256., exact
+                    }
+                    *reinterpret_cast<float4*>(x_out + i0 + 4 * h) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+                }
             } else {
-                for (int j = j_lo; j < j_hi; ++j) x_out[i0 + j] = bm[j];
+                for (int j = j_hi - 1; j >= j_lo; --j) {
+                    pull();
+                    x_out[i0 + j] = (float)decode_symbol(state, bm[j], bs[j], s_tab, flags) * 0.00390625f;
+                }
             }
         }
     }
