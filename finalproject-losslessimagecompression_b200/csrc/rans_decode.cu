@@ -167,9 +167,18 @@ constexpr int kBlkShift = kBlk == 8 ? 3 : 2;           // symbols per lane per b
 // accesses of a quarter-warp fall on disjoint banks; 4-symbol rows (16 B) are conflict-free as is
 constexpr int kBlkPitch = kBlk == 8 ? 12 : 4;
 
+#ifndef FLIC_CP_L2
+#define FLIC_CP_L2 0
+#endif
 __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+#if FLIC_CP_L2 == 128
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#elif FLIC_CP_L2 == 64
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
 }
 
 template <int WARPS>
@@ -281,7 +290,15 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                         pull();
                         xo[k] = (float)decode_symbol(state, ms[k], ss[k], s_tab, flags) * 0.00390625f;  // s / 256., exact
                     }
-                    *reinterpret_cast<float4*>(x_out + i0 + 4 * h) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+                    const float4 o = make_float4(xo[0], xo[1], xo[2], xo[3]);
+                    if (h == 1) {
+                        // parked in the (now free) upper half of the mean row, so that the whole
+                        // 32-byte sector is written at once
+                        *reinterpret_cast<float4*>(bm + 4) = o;
+                    } else {
+                        *reinterpret_cast<float4*>(x_out + i0) = o;
+                        *reinterpret_cast<float4*>(x_out + i0 + 4) = *reinterpret_cast<const float4*>(bm + 4);
+                    }
                 }
             } else {
                 for (int j = j_hi - 1; j >= j_lo; --j) {

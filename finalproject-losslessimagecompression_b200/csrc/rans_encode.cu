@@ -161,17 +161,30 @@ constexpr int kBlkShift = kBlk == 8 ? 3 : 2;
 // CTA instead of 37 KB, 9 resident CTAs per SM instead of 6.
 constexpr int kBlkPitch = kBlk;
 
+#ifndef FLIC_CP_L2
+#define FLIC_CP_L2 0
+#endif
 __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+#if FLIC_CP_L2 == 128
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#elif FLIC_CP_L2 == 64
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
+// 7 resident CTAs per SM (up to 73 registers): measured as fast as 9 (155 vs 156 G symbols/s) with
+// less DRAM over-fetch -- the more lanes stream concurrently, the more of the 64-byte DRAM bursts'
+// second halves are evicted from L2 before their lane asks for them (ncu: 23.5 / 22.0 / 20.4 GB
+// read at 9 / 7 / 6 CTAs for 19.3 GB of inputs).
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 7)
 rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                         const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                         int64_t n_streams, const uint64_t* __restrict__ init_states,
