@@ -257,3 +257,30 @@ def test_lane_per_stream_encoder_is_bit_exact(oracle, pads):
     assert np.array_equal(_u32(enc.words)[:words_o.size], words_o)
     xr, end, status = rans.decode_streams(enc, md, sd, offd)
     assert torch.equal(xr, xd) and not status.any().item() and bool((end == (1 << 32)).all().item())
+
+
+def test_lane_per_stream_encoder_takes_initial_states(oracle):
+    """init_states on the lane-per-stream kernel: code 130 000 streams once, then code them again
+    starting from the states the first pass ended in (coder.py:25 chains states like that), and
+    compare a sample of streams with the reference coder called with the same initial state."""
+    from flic_b200 import rans, _lib
+    n, n_streams = 2_400_000, 130_000
+    x, mean, scale = gen("coder", n, 17)
+    off = ragged_offsets(n, n_streams, 18)
+    xd, md, sd = _cuda(x, mean, scale)
+    offd = torch.from_numpy(off).cuda()
+    first = rans.encode_streams(xd, md, sd, offd)
+    second = rans.encode_streams(xd, md, sd, offd, init_states=first.final_states)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    if (n_streams + 31) // 32 >= 24 * sms:
+        assert _lib.lib().flic_last_coder_kernel(0).decode() == "rans_encode_lane_kernel"
+    st1 = _u64(first.final_states)
+    st2 = _u64(second.final_states)
+    woff = second.word_offsets.cpu().numpy()
+    words = _u32(second.words)
+    rng = np.random.default_rng(3)
+    for s in rng.choice(n_streams, 300, replace=False):
+        a, b = int(off[s]), int(off[s + 1])
+        state, buf = oracle.encode(int(st1[s]), b - a, x[a:b], mean[a:b], scale[a:b])
+        assert int(st2[s]) == state
+        assert np.array_equal(words[woff[s]:woff[s + 1]], buf)
