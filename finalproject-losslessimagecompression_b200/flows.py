@@ -283,8 +283,19 @@ class IDFlows(nn.Module):
         between them.  The bytes produced do not depend on it."""
         if images.dtype != torch.uint8 or images.dim() != 4:
             raise TypeError("images must be uint8 (N, C, H, W)")
-        if tuple(images.shape[1:]) != (self.C, self.H, self.W):
-            raise ValueError(f"model codes {(self.C, self.H, self.W)} images, got {tuple(images.shape[1:])}")
+        return self._compress(images, True, cond, codec_batch, streams_per_segment, check, stats, pipeline)
+
+    def compress_grid(self, x: torch.Tensor, cond: torch.Tensor | None = None, codec_batch: int | None = None,
+                      streams_per_segment: int = 1, check: bool = True, stats: list | None = None,
+                      pipeline: int = 2) -> CompressedBatch:
+        """compress() for inputs that are already on the 2^-nbits grid as float32 (N, C, H, W) --
+        residuals and pooled images of the two-level model (flows.py:212-214) are such tensors and
+        are not 8-bit pixel values."""
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise TypeError("x must be float32 (N, C, H, W) with values on the 2^-nbits grid")
+        return self._compress(x, False, cond, codec_batch, streams_per_segment, check, stats, pipeline)
+
+    def _compress(self, images, from_u8, cond, codec_batch, streams_per_segment, check, stats, pipeline):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise _lib.FlicError("compress needs the model on a CUDA device (no CPU fallback)")
@@ -304,7 +315,7 @@ class IDFlows(nn.Module):
                 with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                     chunk = images[i0:i0 + cbs]
                     n_real = chunk.shape[0]
-                    x = u8_to_grid(chunk)
+                    x = u8_to_grid(chunk) if from_u8 else chunk.contiguous().clone()
                     c = None if cond is None else cond[i0:i0 + cbs]
                     if n_real < cbs:
                         x = torch.cat([x, x.new_zeros((cbs - n_real,) + tuple(x.shape[1:]))])
@@ -331,6 +342,13 @@ class IDFlows(nn.Module):
         flow -> next level's prior), and the decode of a chunk is a few dozen serial streams; with
         pipeline > 1 chunk i runs on CUDA stream i % pipeline, so that chain of one chunk overlaps
         the convolutions of another (level-pipelined decompress)."""
+        return self._decompress(batch, True, cond, check, pipeline)
+
+    def decompress_grid(self, batch, cond: torch.Tensor | None = None, check: bool = True, pipeline: int = 2) -> torch.Tensor:
+        """Inverse of compress_grid: float32 (N, C, H, W) on the 2^-nbits grid."""
+        return self._decompress(batch, False, cond, check, pipeline)
+
+    def _decompress(self, batch, to_u8, cond, check, pipeline):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise _lib.FlicError("decompress needs the model on a CUDA device (no CPU fallback)")
@@ -374,8 +392,11 @@ class IDFlows(nn.Module):
                         x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
                         x = self._flow_backward(block, x)
                         x = block["extend"].backward(x)
-                    img, st8 = grid_to_u8(x[:n_real])
-                    statuses.append(st8)
+                    if to_u8:
+                        img, st8 = grid_to_u8(x[:n_real])
+                        statuses.append(st8)
+                    else:
+                        img = x[:n_real].contiguous()
                     outs.append(img)
                     if side is not None:
                         for t in statuses[-(self.nsplit + 1):]:
@@ -387,7 +408,9 @@ class IDFlows(nn.Module):
         if check:
             for st in statuses:
                 rans.check_status(st)
-        return torch.cat(outs) if outs else torch.empty((0, self.C, self.H, self.W), dtype=torch.uint8, device=dev)
+        if outs:
+            return torch.cat(outs)
+        return torch.empty((0, self.C, self.H, self.W), dtype=torch.uint8 if to_u8 else torch.float32, device=dev)
 
     def _cond_pyramid(self, cond):
         return [None] * self.nsplit
@@ -455,6 +478,107 @@ class ConditionalFlows(IDFlows):
             x = self._flow_backward(block, x.contiguous())
             x = block["extend"].backward(x)
         return x
+
+
+@NNFlows.register
+class TwoLevelFlows(nn.Module):
+    """The reference's two-level model (flows.py:184-274, configs/config_twolevel.yaml): the padded
+    image is average-pooled to a rough image rx = Round(pool(x)) coded by `rough`, and the residual
+    fx = x - upsample(rx), cut into fine.H x fine.W patches (extenddim.Patching), is coded by `fine`.
+    Same constructor, sub-module names (`fine`, `rough`) and latents_shape as the reference, so its
+    checkpoints load.  The reference only trains this wrapper (its forward calls loss.backward and
+    has a typo at :242); here forward is the inference mirror and compress / decompress are real:
+    both parts are multiples of 1/256, the pooling sums are exact in float32 and the upsampling is
+    replication (216 = 8 x 27, 184 = 8 x 23), so x = upsample(rx) + fx holds bit for bit."""
+
+    MAGIC = b"FL2L"
+
+    def __init__(self, H, W, C, pad, fine_flows, rough_flows, batchsize=256, nbits=8):
+        super().__init__()
+        from .extenddim import Patching
+        from .roundlib import Round
+        fine_flows, rough_flows = deepcopy(fine_flows), deepcopy(rough_flows)
+        self.H, self.W, self.C = H + pad[0], W + pad[1], C
+        self.pad = list(pad)
+        self.pad2d = nn.ReplicationPad2d(padding=(0, pad[1], 0, pad[0]))
+        self.fine = NNFlows.get(fine_flows.pop("name"))(**fine_flows)        # construction order of flows.py:198-199
+        self.rough = NNFlows.get(rough_flows.pop("name"))(**rough_flows)
+        self.pool = nn.AdaptiveAvgPool2d((self.rough.H, self.rough.W))
+        self.invpool = nn.AdaptiveAvgPool2d((self.H, self.W))
+        self.patching = Patching(self.H, self.W, self.fine.H, self.fine.W)
+        self.ratio = (self.H // self.fine.H, self.W // self.fine.W)
+        fs = self.fine.latents_shape[0]
+        self.latents_shape = [tuple(self.rough.latents_shape[0]), (fs[0] * self.ratio[0] * self.ratio[1], fs[1], fs[2])]
+        self.batchsize = batchsize
+        self.round = Round(nbits=nbits)
+        if self.H % self.rough.H or self.W % self.rough.W:
+            raise ValueError("padded size must be a multiple of the rough size (exact pooling / replication)")
+
+    # ---- the split x -> (rx, fine patches) and its inverse ------------------------------------
+    def split(self, x: torch.Tensor):
+        """x: (B, C, H - pad0, W - pad1) grid floats -> rx (B, C, rough.H, rough.W), patches (B * n, C, h, w)."""
+        x = self.pad2d(x)
+        rx = self.round(self.pool(x))                     # flows.py:212
+        fx = x - self.invpool(rx)                         # flows.py:213, exact on the grid
+        px, _ = self.patching(fx, None)
+        return rx.contiguous(), px
+
+    def merge(self, rx: torch.Tensor, px: torch.Tensor) -> torch.Tensor:
+        fx = self.patching.backward(px)
+        x = self.invpool(rx) + fx                         # flows.py:261
+        return x[:, :, :x.shape[2] - self.pad[0], :x.shape[3] - self.pad[1]].contiguous()
+
+    @torch.no_grad()
+    def forward(self, x, logv=None, train=False):
+        """Inference mirror of flows.py:206-246: latents / means / logscales of both levels and
+        the ideal bits per dimension (total, rough, fine)."""
+        if train:
+            raise NotImplementedError("training is outside the coding path")
+        rx, px = self.split(x)
+        rl, rm, rs, logv = self.rough.forward(rx, logv)
+        logp, _ = self.rough.log_likelihood(rl, rm, rs)
+        bpd1 = float(torch.mean(-logp)) / math.log(2)
+        fl, fm, fs, bpd2 = [], [], [], 0.0
+        for i0 in range(0, px.shape[0], self.batchsize):
+            l, m, sc, logv = self.fine.forward(px[i0:i0 + self.batchsize], logv)
+            logp, _ = self.fine.log_likelihood(l, m, sc)
+            bpd2 += float(torch.sum(-logp)) / math.log(2)
+            fl.append(l[0]); fm.append(m[0]); fs.append(sc[0])
+        bpd2 /= px.shape[0]
+        bpd = ((bpd1 * self.rough.H * self.rough.W + bpd2 * self.H * self.W)
+               / (self.H - self.pad[0]) / (self.W - self.pad[1]))                       # flows.py:240
+        return ([rl[0], torch.cat(fl)], [rm[0], torch.cat(fm)], [rs[0], torch.cat(fs)], bpd, bpd1, bpd2, logv)
+
+    def inverse(self):
+        self.fine.inverse()
+        self.rough.inverse()
+
+    # ---- compress / decompress ---------------------------------------------------------------------
+    def compress(self, images: torch.Tensor, rough_batch: int | None = None, check: bool = True) -> bytes:
+        """uint8 (N, C, H - pad0, W - pad1) -> bytes: the rough container followed by the fine one
+        (one rANS stream per rough image and one per fine patch)."""
+        if images.dtype != torch.uint8 or images.dim() != 4:
+            raise TypeError("images must be uint8 (N, C, H, W)")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.FlicError("compress needs the model on a CUDA device (no CPU fallback)")
+        rx, px = self.split(u8_to_grid(images.to(dev)))
+        rough = self.rough.compress_grid(rx, codec_batch=rough_batch or rx.shape[0], check=check).to_bytes()
+        fine = self.fine.compress_grid(px, codec_batch=self.batchsize, check=check).to_bytes()
+        return self.MAGIC + len(rough).to_bytes(8, "little") + rough + fine
+
+    def decompress(self, blob: bytes, check: bool = True) -> torch.Tensor:
+        if bytes(blob[:4]) != self.MAGIC or len(blob) < 12:
+            raise ValueError("not a two-level container")
+        n_rough = int.from_bytes(blob[4:12], "little")
+        if 12 + n_rough > len(blob):
+            raise ValueError("truncated two-level container")
+        rx = self.rough.decompress_grid(bytes(blob[12:12 + n_rough]), check=check)
+        px = self.fine.decompress_grid(bytes(blob[12 + n_rough:]), check=check)
+        img, status = grid_to_u8(self.merge(rx, px))
+        if check:
+            rans.check_status(status)
+        return img
 
 
 def build_model(cfg: dict) -> nn.Module:

@@ -586,3 +586,27 @@ def test_config_vqvae_conditional_patches(oracle):
     assert batch.n_streams() == n
     _check_streams_against_oracle(oracle, model, batch, stats, n, 1)
     assert torch.equal(model.decompress(batch.to_bytes(), cond=cond), patches)
+
+
+def test_twolevel_flows_compress_decompress(oracle):
+    """configs/config_twolevel.yaml shapes (215 x 178 images padded to 216 x 184, rough 27 x 23,
+    621 fine 8 x 8 patches per image; narrow networks): bytes -> pixels round trip, and the
+    reference-style forward reports finite ideal bits per dimension."""
+    from test_host_logic import twolevel_cfg
+    import random
+    from flic_b200 import flows
+    torch.manual_seed(0)
+    random.seed(0)
+    model = flows.build_model(twolevel_cfg())
+    flows.perturb_heads(model, 0.02)
+    model = model.cuda().eval()
+    img = torch.randint(0, 256, (3, 3, 215, 178), dtype=torch.uint8, generator=torch.Generator().manual_seed(2)).cuda()
+    blob = model.compress(img)
+    assert torch.equal(model.decompress(blob), img)
+    lat, means, logs, bpd, bpd1, bpd2, _ = model.forward(flows.u8_to_grid(img))
+    assert lat[0].shape == (3, 3, 27, 23) and lat[1].shape == (3 * 621, 12, 4, 4)
+    assert np.isfinite(bpd) and bpd > 0
+    real_bpd = 8 * len(blob) / img.numel()
+    assert real_bpd >= bpd - 1e-3 and real_bpd < bpd * 1.02 + 64 * (3 + 3 * 621) / img.numel() + 0.05
+    with pytest.raises(ValueError):
+        model.decompress(b"XXXX" + blob[4:])

@@ -173,3 +173,45 @@ def test_oracle_reproduces_reference_coding_loop(oracle):
         assert state == int(g["id.states"][i]) and np.array_equal(buf, g[f"id.words{i}"])
         total_words += buf.size
     assert (64 * 2 + 32 * total_words) / g["id.x"].size == float(g["id.real_bpd"])
+
+
+# ---- TwoLevelFlows (flows.py:184-274, configs/config_twolevel.yaml) ------------------------------
+
+def twolevel_cfg():
+    layer = dict(name="DenseLayer", act="ReLU")
+
+    def sub(H, W, scale, nflows):
+        return dict(name="IDFlows", nflows=nflows, nbits=8, nsplit=1, H=H, W=W, C=3,
+                    couple=dict(name="AdditiveCouple", split=0.75, round=dict(name="Round", nbits=8),
+                                nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=dict(layer))),
+                    extenddim=dict(name="ExtendDim", scale=scale),
+                    prior=dict(name="Prior", round=dict(name="Round", nbits=8),
+                               nn=dict(name="DenseBlock", growth_channel=16, depth=2, layer=dict(layer))),
+                    distribution=dict(name="DLogistic"), round=dict(name="Round", nbits=8))
+    return dict(name="TwoLevelFlows", H=215, W=178, C=3, pad=[1, 6], fine_flows=sub(8, 8, 2, 3),
+                rough_flows=sub(27, 23, 1, 3), batchsize=1536)
+
+
+def test_twolevel_structure_and_split_match_the_reference():
+    """Same seeds -> the reference's state_dict (names, shapes, values: construction order), the
+    same latents_shape, and the same rough image / residual patches for the same input
+    (tests/golden/twolevel.json was produced by the reference's own TwoLevelFlows)."""
+    import json
+    from flic_b200 import flows
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "twolevel.json")))
+    torch.manual_seed(0)
+    random.seed(0)
+    model = flows.build_model(twolevel_cfg()).eval()
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == sorted(g["state"].keys())
+    for k, (shape, total) in g["state"].items():
+        assert list(sd[k].shape) == shape, k
+        assert abs(float(sd[k].double().sum()) - total) <= 1e-9 * max(1.0, abs(total)), k
+    assert [list(s) for s in model.latents_shape] == g["latents_shape"]
+    u8 = torch.randint(0, 256, (2, 3, 215, 178), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    x = torch.round(u8.float() / 255 * 256) / 256
+    rx, px = model.split(x)
+    assert list(px.shape) == g["px_shape"]
+    assert float(rx.double().sum()) == g["rx_sum"] and rx[0, 0, 0, :8].tolist() == g["rx_head"]
+    assert float(px.double().abs().sum()) == g["px_abs_sum"] and px[5].flatten().tolist() == g["px_patch5"]
+    assert torch.equal(model.merge(rx, px), x)               # x = upsample(rx) + fx, exactly
