@@ -586,6 +586,12 @@ def test_config_vqvae_conditional_patches(oracle):
     assert batch.n_streams() == n
     _check_streams_against_oracle(oracle, model, batch, stats, n, 1)
     assert torch.equal(model.decompress(batch.to_bytes(), cond=cond), patches)
+    # the residual path of the reference's ResidualTrainer (trainer.py:606-621): what is coded is
+    # image - reconstruction, a grid-valued float tensor with negative entries, under the same cond
+    resid = flows.u8_to_grid(patches) - cond
+    assert float(resid.min()) < 0
+    blob = model.compress_grid(resid, cond=cond, codec_batch=48).to_bytes()
+    assert torch.equal(model.decompress_grid(blob, cond=cond), resid)
 
 
 def test_twolevel_flows_compress_decompress(oracle):
