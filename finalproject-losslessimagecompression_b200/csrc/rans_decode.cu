@@ -162,23 +162,14 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
 #define FLIC_LANE_BLOCK 8
 #endif
 constexpr int kBlk = FLIC_LANE_BLOCK;   // symbols per lane per block: 8 (one 32-byte sector) or 4
-constexpr int kBlkShift = kBlk == 8 ? 3 : 2;           // symbols per lane per block (32 bytes)
+constexpr int kBlkShift = kBlk == 8 ? 3 : 2;
 // floats per lane row in shared memory: 8-symbol rows are padded to 48 B so that the 16-byte
 // accesses of a quarter-warp fall on disjoint banks; 4-symbol rows (16 B) are conflict-free as is
 constexpr int kBlkPitch = kBlk == 8 ? 12 : 4;
 
-#ifndef FLIC_CP_L2
-#define FLIC_CP_L2 0
-#endif
 __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-#if FLIC_CP_L2 == 128
-    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#elif FLIC_CP_L2 == 64
-    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#endif
 }
 
 template <int WARPS>

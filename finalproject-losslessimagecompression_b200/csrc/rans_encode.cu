@@ -147,7 +147,7 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
 // not needed: a lane stages 32-byte blocks of ITS stream's x / mean / scale with 16-byte cp.async
 // (one DRAM sector per array per 8 symbols), evaluates the eight table entries and pushes them
 // through its rANS state in the same loop.  No CTA barriers, no role imbalance, no tile
-// transposes: ~190 instructions per symbol instead of ~215.  Blocks are cut on the 32-byte grid
+// transposes: ~170 instructions per 32 symbols instead of ~215.  Blocks are cut on the 32-byte grid
 // of the arrays' addresses (see rans_decode.cu); the launcher picks this kernel only when the
 // three arrays share the same phase.
 #ifndef FLIC_LANE_BLOCK
@@ -158,21 +158,12 @@ constexpr int kBlkShift = kBlk == 8 ? 3 : 2;
 // A lane's row in shared memory is exactly its block (32 B or 16 B).  For 8-symbol rows the two
 // 16-byte halves of rows 4..7, 12..15, ... are swapped (XOR swizzle on bit 2 of the column), which
 // puts the 16-byte accesses of every quarter-warp on disjoint banks without padding: 24.6 KB per
-// CTA instead of 37 KB, 9 resident CTAs per SM instead of 6.
+// CTA instead of 37 KB, so shared memory no longer limits residency.
 constexpr int kBlkPitch = kBlk;
 
-#ifndef FLIC_CP_L2
-#define FLIC_CP_L2 0
-#endif
 __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-#if FLIC_CP_L2 == 128
-    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#elif FLIC_CP_L2 == 64
-    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#endif
 }
 __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
