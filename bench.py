@@ -363,7 +363,7 @@ def run_flic(args) -> dict | None:
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 5), "peak_source": peaks["source"],
                 "algorithmic_bytes_per_symbol": round(alg_bytes, 4), "symbols_per_launch": n,
-                "avg_launch_ms": round(dom_ms, 4), "traffic": read_traffic(dom_name, n),
+                "avg_launch_ms": round(dom_ms, 4), "traffic": read_traffic(dom_name, n), "issue": read_issue(dom_name),
                 "encode_ms": round(enc_ms, 4), "decode_ms": round(dec_ms, 4),
                 "encode_kernel": enc_kernel, "decode_kernel": dec_kernel,
                 "encode_GBps_algorithmic": round(n * alg_bytes / (enc_ms * 1e-3) / 1e9, 2),
@@ -522,6 +522,19 @@ def read_peaks():
         return {"hbm_gbs": float(p["hbm_gbs"]), "source": "MEASURED_PEAKS.json (measured copy bandwidth)"}
     except Exception:
         return {"hbm_gbs": 6650.0, "source": "fallback 6.65 TB/s (B200_PROFILING.md)"}
+
+
+def read_issue(kernel: str):
+    """Instruction-issue evidence of the dominant kernel from the committed ncu capture: the coder is
+    bound by issue slots on exact FP64 arithmetic, not by HBM, so this is what explains roofline.frac."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        rec = t[kernel.split(" ")[0]]
+        wi = float(rec["warp_instructions_per_symbol"])
+        return {"warp_instructions_per_symbol": wi, "issue_slots_busy_pct": rec.get("issue_slots_busy_pct"),
+                "issue_ceiling_Gsymbols_per_s": round(148 * 4 * 1.965 / wi, 1), "source": rec["from"] + " (ncu --set full)"}
+    except Exception:
+        return None
 
 
 def read_traffic(kernel: str, n_symbols: int):

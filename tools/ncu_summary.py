@@ -62,7 +62,10 @@ def main():
                 mix[op.split(".")[0]] += int(s[ia])
             rec["thread_instructions_per_symbol_by_opcode"] = {op: round(32 * c / n_sym, 2) for op, c in mix.most_common(24)}
         out[name] = rec
-        traffic[short] = {"dram_bytes_per_symbol": rec["dram_bytes_per_symbol"], "from": f"profiles/{tag}_ncu_full_summary.json"}
+        traffic[short] = {"dram_bytes_per_symbol": rec["dram_bytes_per_symbol"],
+                          "warp_instructions_per_symbol": rec["warp_instructions_per_symbol"],
+                          "issue_slots_busy_pct": float(rec.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan").split()[0]),
+                          "from": f"profiles/{tag}_ncu_full_summary.json"}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     json.dump({"command": cmd, "symbols_per_launch": n_sym, "kernels": out},
               open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.json"), "w"), indent=1)
