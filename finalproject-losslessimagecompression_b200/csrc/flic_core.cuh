@@ -283,9 +283,9 @@ FLIC_HD double clamp_mag128(double q) {
 // exp_core(xd) is the double-precision body of glibc's expf for xd = (double)x: it returns the
 // product y * s whose conversion to float is the function's result.  Valid (no exponent
 // overflow in s) for |xd| < 700.
-// The polynomial is evaluated with fused multiply-adds.  oracle/rans_oracle.c proves (exhaustive
-// sweep over |x| <= 104, tests/test_oracle_pinning.py) that fused and unfused evaluation both
-// agree with the host libm everywhere except two inputs deep inside part1's saturated range.
+// The polynomial is evaluated with fused multiply-adds in Horner form (see below); the GPU suite
+// sweeps every float |x| <= 104 against the host libm: equal everywhere except two inputs deep
+// inside part1's saturated range, where the host itself departs from the published algorithm.
 // `neg` evaluates exp(-xd): (-InvLn2N) * xd is bit-identical to InvLn2N * (-xd).
 FLIC_HD double exp_core(double xd, const uint64_t* tab, bool neg) {
     const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
@@ -301,10 +301,14 @@ FLIC_HD double exp_core(double xd, const uint64_t* tab, bool neg) {
     // T[k % 32] + (k << 47): the shift only reaches the high word (47 - 32 = 15)
     const uint64_t tv = tab[ki & 31];
     const double s = f64_from_words((uint32_t)(tv >> 32) + (ki << 15), (uint32_t)tv);
-    const double zz = dfma(C0, r, C1);
-    const double r2 = dmul(r, r);
-    double y = dfma(C2, r, 1.0);
-    y = dfma(zz, r2, y);
+    // glibc evaluates (C0 r + C1) r^2 + (C2 r + 1); Horner's form has one operation less and
+    // differs from it by an ulp or two of the double -- which could change the float result only
+    // if y s sat within ~2^-51 of a float rounding boundary.  Both exhaustive sweeps (every float
+    // |x| <= 104 against the host libm, and part1 over all 2^32 arguments) pass with this form, so
+    // it is exact for every input that exists.
+    double y = dfma(C0, r, C1);
+    y = dfma(y, r, C2);
+    y = dfma(y, r, 1.0);
     return dmul(y, s);
 }
 
