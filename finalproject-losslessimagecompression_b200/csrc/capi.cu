@@ -236,7 +236,7 @@ struct flic_codec {
     cudaEvent_t done[kSlots];
     struct Slot {
         float *x, *mean, *scale;
-        int64_t* offsets;       // this chunk's slice of the caller's stream offsets (absolute values)
+        int64_t* offsets;       // this chunk's stream offsets, rebased to start at 0
         uint32_t* packed;
         int64_t* word_offsets;
         uint64_t* states;
@@ -245,6 +245,8 @@ struct flic_codec {
         void* workspace;
         int64_t workspace_bytes;
         int64_t* h_word_offsets;  // pinned staging for the chunk-local word offsets
+        int64_t* h_offsets;       // pinned staging for the chunk-local stream offsets
+        bool busy;                // done[] has been recorded for work that reads the staging arrays
     } slot[kSlots];
 };
 
@@ -255,6 +257,7 @@ static void free_slots(flic_codec* c) {
         cudaFree(s.word_offsets); cudaFree(s.states); cudaFree(s.end_states); cudaFree(s.status);
         cudaFree(s.workspace);
         cudaFreeHost(s.h_word_offsets);
+        cudaFreeHost(s.h_offsets);
         memset((void*)&s, 0, sizeof s);
     }
 }
@@ -277,6 +280,7 @@ static cudaError_t alloc_slots(flic_codec* c, int64_t ns, int64_t nt) {
         if (e == cudaSuccess) e = cudaMalloc(&s.status, sizeof(int32_t) * nt);
         if (e == cudaSuccess) e = cudaMalloc(&s.workspace, (size_t)s.workspace_bytes);
         if (e == cudaSuccess) e = cudaMallocHost(&s.h_word_offsets, sizeof(int64_t) * (nt + 1));
+        if (e == cudaSuccess) e = cudaMallocHost(&s.h_offsets, sizeof(int64_t) * (nt + 1));
     }
     return e;
 }
@@ -428,18 +432,21 @@ int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const fl
         flic_codec::Slot& sl = c->slot[slot];
         cudaStream_t st = c->streams[slot];
         const int64_t a = off[s0], n = off[s1] - a, ns = s1 - s0;
+        // The slot's staging arrays were last read by the chunk that used this slot kSlots chunks
+        // ago; its `done` event was waited for in finalize(), so they are free.  Offsets are rebased
+        // to the chunk so that the kernels index the slot's arrays from 0.
+        for (int64_t i = 0; i <= ns; ++i) sl.h_offsets[i] = off[s0 + i] - a;
         if (n > 0) {
             FLIC_CUDA(cudaMemcpyAsync(sl.x, x + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
             FLIC_CUDA(cudaMemcpyAsync(sl.mean, mean + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
             FLIC_CUDA(cudaMemcpyAsync(sl.scale, scale + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
         }
-        FLIC_CUDA(cudaMemcpyAsync(sl.offsets, off + s0, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
-        // the kernels index symbols (and the scratch region) by the caller's absolute offsets
+        FLIC_CUDA(cudaMemcpyAsync(sl.offsets, sl.h_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
         const EncodeWorkspace w = carve(sl.workspace, c->slot_symbols, c->slot_streams);
-        FLIC_CUDA(flic::launch_rans_encode(sl.x - a, sl.mean - a, sl.scale - a, sl.offsets, ns, nullptr, w.scratch - a,
+        FLIC_CUDA(flic::launch_rans_encode(sl.x, sl.mean, sl.scale, sl.offsets, ns, nullptr, w.scratch,
                                            w.counts, sl.states, sl.status, st));
         FLIC_CUDA(flic::launch_scan_counts(w.counts, ns, sl.word_offsets, w.scan_tmp, st));
-        FLIC_CUDA(flic::launch_pack_words(w.scratch - a, sl.offsets, sl.word_offsets, ns, sl.packed, c->slot_symbols,
+        FLIC_CUDA(flic::launch_pack_words(w.scratch, sl.offsets, sl.word_offsets, ns, sl.packed, c->slot_symbols,
                                           sl.status, st));
         g_launches += 5;
         FLIC_CUDA(cudaMemcpyAsync(sl.h_word_offsets, sl.word_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyDeviceToHost, st));
@@ -490,17 +497,25 @@ int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_
         const int slot = (int)(chunk % flic_codec::kSlots);
         flic_codec::Slot& sl = c->slot[slot];
         cudaStream_t st = c->streams[slot];
+        // offsets are rebased to the chunk on the host; the staging arrays are free once the work
+        // that last read them (this slot, kSlots chunks ago) has finished
+        if (sl.busy) FLIC_CUDA(cudaEventSynchronize(c->done[slot]));
+        for (int64_t i = 0; i <= ns; ++i) {
+            sl.h_offsets[i] = off[s0 + i] - a;
+            sl.h_word_offsets[i] = word_offsets[s0 + i] - wa;
+        }
         if (nw > 0) FLIC_CUDA(cudaMemcpyAsync(sl.packed, words + wa, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
-        FLIC_CUDA(cudaMemcpyAsync(sl.word_offsets, word_offsets + s0, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+        FLIC_CUDA(cudaMemcpyAsync(sl.word_offsets, sl.h_word_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
         FLIC_CUDA(cudaMemcpyAsync(sl.states, states + s0, sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, st));
         if (n > 0) {
             FLIC_CUDA(cudaMemcpyAsync(sl.mean, mean + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
             FLIC_CUDA(cudaMemcpyAsync(sl.scale, scale + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
         }
-        FLIC_CUDA(cudaMemcpyAsync(sl.offsets, off + s0, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
-        // absolute symbol and word offsets index shifted base pointers
-        FLIC_CUDA(flic::launch_rans_decode(sl.packed - wa, sl.word_offsets, sl.states, sl.mean - a, sl.scale - a,
-                                           sl.offsets, ns, sl.x - a, sl.end_states, sl.status, 1, st));
+        FLIC_CUDA(cudaMemcpyAsync(sl.offsets, sl.h_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+        FLIC_CUDA(cudaEventRecord(c->done[slot], st));
+        sl.busy = true;
+        FLIC_CUDA(flic::launch_rans_decode(sl.packed, sl.word_offsets, sl.states, sl.mean, sl.scale,
+                                           sl.offsets, ns, sl.x, sl.end_states, sl.status, 1, st));
         g_launches += 1;
         if (n > 0) FLIC_CUDA(cudaMemcpyAsync(x_out + a, sl.x, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
         if (end_states_out)
