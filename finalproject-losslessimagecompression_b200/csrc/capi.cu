@@ -369,16 +369,28 @@ static int check_offsets(const int64_t* off, int64_t n_streams) {
     return 0;
 }
 
-// Last stream (exclusive) of the chunk that starts at s0: as many whole streams as fit a slot.
-// Returns s0 when the first stream alone is larger than a slot.
-static int64_t chunk_end(const flic_codec* c, const int64_t* off, int64_t n_streams, int64_t s0) {
+// Last stream (exclusive) of the chunk that starts at s0: as many whole streams as fit `cap`
+// symbols (at most a slot).  Returns s0 when the first stream alone is larger than a slot.
+static int64_t chunk_end(const flic_codec* c, const int64_t* off, int64_t n_streams, int64_t s0, int64_t cap) {
     int64_t lo = s0, hi = n_streams < s0 + c->slot_streams ? n_streams : s0 + c->slot_streams;
-    const int64_t limit = off[s0] + c->slot_symbols;
+    const int64_t limit = off[s0] + cap;
     while (lo < hi) {  // largest s1 in (s0, hi] with off[s1] <= limit
         const int64_t mid = lo + (hi - lo + 1) / 2;
         if (off[mid] <= limit) lo = mid; else hi = mid - 1;
     }
+    if (lo == s0 && s0 < n_streams && off[s0 + 1] - off[s0] <= c->slot_symbols) lo = s0 + 1;   // one stream above the cap still fits a slot
     return lo;
+}
+
+// Symbols to aim for in the chunk starting at symbol `done` of `total`: the pipeline's fill (nothing
+// to overlap the first upload with) and drain (nothing overlaps the last kernels and download)
+// cost one chunk each, so the first chunk is an eighth of a slot and the last ones halve.
+static int64_t chunk_cap(const flic_codec* c, int64_t chunk, int64_t done, int64_t total) {
+    const int64_t small = c->slot_symbols / 8 > 0 ? c->slot_symbols / 8 : 1;
+    if (chunk == 0) return small;
+    int64_t cap = (total - done) / 2;
+    if (cap < small) cap = small;
+    return cap < c->slot_symbols ? cap : c->slot_symbols;
 }
 
 int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const float* scale,
@@ -422,11 +434,11 @@ int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const fl
 
     int64_t s0 = 0;
     for (int64_t chunk = 0; s0 < n_streams; ++chunk) {
-        int64_t s1 = chunk_end(c, off, n_streams, s0);
+        int64_t s1 = chunk_end(c, off, n_streams, s0, chunk_cap(c, chunk, off[s0], n_symbols));
         if (s1 == s0) {  // one stream larger than a slot: finish what is in flight, grow, retry
             if (prev.active) { if (int rc = finalize(prev)) return rc; prev.active = false; }
             if (int rc = ensure_slot_symbols(c, off[s0 + 1] - off[s0])) return rc;
-            s1 = chunk_end(c, off, n_streams, s0);
+            s1 = chunk_end(c, off, n_streams, s0, c->slot_symbols);
         }
         const int slot = (int)(chunk % flic_codec::kSlots);
         flic_codec::Slot& sl = c->slot[slot];
@@ -484,10 +496,10 @@ int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_
     const int64_t* off = stream_offsets;
     int64_t s0 = 0;
     for (int64_t chunk = 0; s0 < n_streams; ++chunk) {
-        int64_t s1 = chunk_end(c, off, n_streams, s0);
+        int64_t s1 = chunk_end(c, off, n_streams, s0, chunk_cap(c, chunk, off[s0], n_symbols));
         if (s1 == s0) {
             if (int rc = ensure_slot_symbols(c, off[s0 + 1] - off[s0])) return rc;
-            s1 = chunk_end(c, off, n_streams, s0);
+            s1 = chunk_end(c, off, n_streams, s0, c->slot_symbols);
         }
         const int64_t a = off[s0], n = off[s1] - a, ns = s1 - s0;
         const int64_t wa = word_offsets[s0], nw = word_offsets[s1] - wa;
