@@ -36,6 +36,8 @@ SIGNATURES = {
     "flic_cdf_tables": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_debug_expf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "flic_debug_part1": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "flic_debug_div_check": (C.c_int, [_i64, _u64, C.c_int, _vp, _vp]),
+    "flic_debug_push_check": (C.c_int, [_i64, _u64, _vp, _vp]),
     "flic_dlogistic_log_prob": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, C.c_float, _vp, _vp, _vp]),
     "flic_dlogistic_sample": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp, _vp]),
     "flic_encode_workspace_bytes": (_i64, [_i64, _i64]),

@@ -97,6 +97,20 @@ int flic_debug_part1(const float* arg, int32_t* y, int64_t n, flic_cuda_stream_t
     return 0;
 }
 
+int flic_debug_div_check(int64_t n, uint64_t seed, int mode, uint64_t* mismatches, flic_cuda_stream_t stream) {
+    if (n < 0 || !mismatches || (mode != 0 && mode != 1)) return fail(FLIC_E_ARG, "bad argument");
+    FLIC_CUDA(flic::launch_debug_div_check(n, seed, mode, (unsigned long long*)mismatches, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int flic_debug_push_check(int64_t n, uint64_t seed, uint64_t* mismatches, flic_cuda_stream_t stream) {
+    if (n < 0 || !mismatches) return fail(FLIC_E_ARG, "bad argument");
+    FLIC_CUDA(flic::launch_debug_push_check(n, seed, (unsigned long long*)mismatches, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
 int64_t flic_encode_workspace_bytes(int64_t n_symbols, int64_t n_streams) {
     return carve(nullptr, n_symbols, n_streams).bytes;
 }

@@ -67,6 +67,92 @@ cudaError_t launch_debug_part1(const float* arg, int32_t* y, int64_t n, cudaStre
     return cudaGetLastError();
 }
 
+// Diagnostics: the two reciprocal-based divisions of the coder against the hardware's own exact
+// division, on operands drawn the way the coder produces them (counter-based generator, so a
+// test can cover 2^32 cases in a second).  mismatches is a device counter.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// mode 0: realistic magnitudes (|mean| <= 4, scale in [2^-37, 2^22], symbol inside its window);
+// mode 1: any finite positive float scale (subnormals included), any float mean with |mean| <= 16384,
+//         any symbol index below 2^22.
+__global__ void __launch_bounds__(256)
+debug_div_check_kernel(int64_t n, uint64_t seed, int mode, unsigned long long* __restrict__ mismatches) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r1 = splitmix64(seed + 3 * (uint64_t)i), r2 = splitmix64(seed + 3 * (uint64_t)i + 1),
+                       r3 = splitmix64(seed + 3 * (uint64_t)i + 2);
+        float mean, scale;
+        int k;
+        if (mode == 0) {
+            mean = (float)((double)(int64_t)(r1 % 2000001) / 1000000.0 - 1.0) * 4.0f;
+            const uint32_t bits = ((90u + (uint32_t)(r2 % 60)) << 23) | (uint32_t)(r2 >> 41);
+            scale = __uint_as_float(bits);
+            k = (int)(r3 % 4097) - 2048 + (int)(mean * 256.0f);
+        } else {
+            mean = __uint_as_float((uint32_t)r1);
+            if (!(fabsf(mean) <= 16384.0f)) mean = 0.25f;
+            uint32_t bits = (uint32_t)(r2 >> 33);
+            if (bits == 0 || bits >= 0x7f800000u) bits = 0x3f800001u;
+            scale = __uint_as_float(bits);
+            k = (int)(r3 % 8388608) - 4194304;
+        }
+        const SymbolModel m = make_model(mean, scale);
+        const double a = dsub(half_bin_point(k), m.mean_d);
+        const double q = div_by_scale(a, m);
+        const double want = __ddiv_rn(a, (double)scale);
+        bad += (__double_as_longlong(q) != __double_as_longlong(want));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// rans_push against 64-bit integer division over (state, freq) pairs that satisfy the coder's
+// invariants (2^32 <= state < 2^64, 1 <= freq <= 2^24, start + freq <= 2^24).
+__global__ void __launch_bounds__(256)
+debug_push_check_kernel(int64_t n, uint64_t seed, unsigned long long* __restrict__ mismatches) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r1 = splitmix64(seed + 3 * (uint64_t)i), r2 = splitmix64(seed + 3 * (uint64_t)i + 1),
+                       r3 = splitmix64(seed + 3 * (uint64_t)i + 2);
+        uint32_t freq = (uint32_t)(r1 % 16777216) + 1;                    // 1 .. 2^24
+        if ((r3 & 7) == 0) freq = (uint32_t)(r3 >> 8) % 64 + 1;           // small frequencies too
+        if ((r3 & 0xf00) == 0) freq = 1u << ((r3 >> 12) % 25);            // powers of two
+        uint64_t state = r2 | 0x100000000ull;                             // any state >= 2^32
+        if ((r3 & 0x30) == 0) state = ((uint64_t)freq << 40) - 1 - (r2 & 0xffff);   // just below a renormalisation
+        if ((r3 & 0xc0) == 0) state = ((uint64_t)freq << 40) + (r2 & 0xffff);       // just above
+        const uint32_t start = (uint32_t)((r3 >> 40) % (16777216u - freq + 1));
+        // what the reference does (rans.pyx:62-65)
+        uint64_t ref = state;
+        uint32_t ref_word = 0;
+        bool ref_emit = false;
+        if (ref >= ((uint64_t)freq << 40)) { ref_word = (uint32_t)ref; ref >>= 32; ref_emit = true; }
+        ref = ((ref / freq) << 24) + (ref % freq) + start;
+        uint64_t st = state;
+        uint32_t word = 0;
+        const bool emit = rans_push(st, start, freq, word);
+        bad += (st != ref) || (emit != ref_emit) || (emit && word != ref_word);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_debug_div_check(int64_t n, uint64_t seed, int mode, unsigned long long* mismatches, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    debug_div_check_kernel<<<sm_count() * 8, 256, 0, stream>>>(n, seed, mode, mismatches);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_debug_push_check(int64_t n, uint64_t seed, unsigned long long* mismatches, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    debug_push_check_kernel<<<sm_count() * 8, 256, 0, stream>>>(n, seed, mismatches);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_debug_expf(const float* x, float* y, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     int64_t blocks = (n + 255) / 256;

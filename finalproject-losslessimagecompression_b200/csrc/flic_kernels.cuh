@@ -23,6 +23,8 @@ cudaError_t launch_cdf_tables(const float* x, const float* mean, const float* sc
 
 cudaError_t launch_debug_expf(const float* x, float* y, int64_t n, cudaStream_t stream);
 cudaError_t launch_debug_part1(const float* arg, int32_t* y, int64_t n, cudaStream_t stream);
+cudaError_t launch_debug_div_check(int64_t n, uint64_t seed, int mode, unsigned long long* mismatches, cudaStream_t stream);
+cudaError_t launch_debug_push_check(int64_t n, uint64_t seed, unsigned long long* mismatches, cudaStream_t stream);
 
 // K1+K2 fused: per-stream rANS encode into worst-case scratch regions.
 //   scratch[offsets[s] .. offsets[s] + counts[s])  = words of stream s in emission order

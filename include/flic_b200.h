@@ -79,6 +79,16 @@ int flic_debug_expf(const float* x, float* y, int64_t n, flic_cuda_stream_t stre
  * of CDF() after the division.  A function of 32 bits, so tests sweep all of them. */
 int flic_debug_part1(const float* arg, int32_t* y, int64_t n, flic_cuda_stream_t stream);
 
+/* Diagnostics: the two divisions the coder does with reciprocals, checked on the device against the
+ * hardware's exact division over n generated operand pairs; *mismatches (uint64, device, caller
+ * zeroes it) receives the number of disagreements.
+ *   div_check:  (xq + 1/512 - mean) / scale of CDF(), rans/rans.pyx:34 (rans.cpp:1434-1439);
+ *               mode 0 = realistic magnitudes, 1 = any finite positive scale / any |mean| <= 16384
+ *   push_check: the encoder step state -> (state / freq << 24) + state % freq + start with its
+ *               renormalisation, rans/rans.pyx:62-65 */
+int flic_debug_div_check(int64_t n, uint64_t seed, int mode, uint64_t* mismatches, flic_cuda_stream_t stream);
+int flic_debug_push_check(int64_t n, uint64_t seed, uint64_t* mismatches, flic_cuda_stream_t stream);
+
 /* Bytes of device workspace flic_rans_encode needs (worst-case word scratch + scan temporaries). */
 int64_t flic_encode_workspace_bytes(int64_t n_symbols, int64_t n_streams);
 

@@ -284,3 +284,19 @@ def test_lane_per_stream_encoder_takes_initial_states(oracle):
         state, buf = oracle.encode(int(st1[s]), b - a, x[a:b], mean[a:b], scale[a:b])
         assert int(st2[s]) == state
         assert np.array_equal(words[woff[s]:woff[s + 1]], buf)
+
+
+def test_reciprocal_divisions_are_exact_on_the_device():
+    """The coder never divides: t4 / scale is a cubic-step reciprocal plus one exact-remainder
+    correction, state / freq a low-biased reciprocal plus one integer correction (DESIGN.md
+    section 2).  Both are checked on the GPU against the hardware's exact divisions over 2^31
+    generated operand pairs each (realistic and adversarial ranges)."""
+    import ctypes as C
+    from flic_b200 import _lib
+    L = _lib.lib()
+    n = 1 << 31
+    bad = torch.zeros(3, dtype=torch.int64, device="cuda")
+    _lib.check(L.flic_debug_div_check(n, C.c_uint64(1), 0, bad[0:1].data_ptr(), None))
+    _lib.check(L.flic_debug_div_check(n, C.c_uint64(2), 1, bad[1:2].data_ptr(), None))
+    _lib.check(L.flic_debug_push_check(n, C.c_uint64(3), bad[2:3].data_ptr(), None))
+    assert bad.tolist() == [0, 0, 0]
