@@ -247,22 +247,24 @@ rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ m
             const int j_hi = i0 + kBlk <= end ? kBlk : (int)(end - i0);
             if (kBlk == 8 && j_lo == 0 && j_hi == kBlk) {
                 // whole block: the row comes out of shared memory as 16-byte vectors (conflict-free
-                // by the swizzle) and the four symbols of each half are coded from registers
-#pragma unroll 1
+                // by the swizzle) and its eight symbols are coded from registers, fully unrolled, so
+                // that the table evaluations of later symbols fill the latencies of earlier pushes
+                float xs[8], ms[8], ss[8];
+#pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int c = (4 * h) ^ swz;
                     const float4 xv = *reinterpret_cast<const float4*>(b + c);
                     const float4 mv = *reinterpret_cast<const float4*>(b + kArr + c);
                     const float4 sv = *reinterpret_cast<const float4*>(b + 2 * kArr + c);
-                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const float ms[4] = {mv.x, mv.y, mv.z, mv.w};
-                    const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
+                    xs[4 * h] = xv.x; xs[4 * h + 1] = xv.y; xs[4 * h + 2] = xv.z; xs[4 * h + 3] = xv.w;
+                    ms[4 * h] = mv.x; ms[4 * h + 1] = mv.y; ms[4 * h + 2] = mv.z; ms[4 * h + 3] = mv.w;
+                    ss[4 * h] = sv.x; ss[4 * h + 1] = sv.y; ss[4 * h + 2] = sv.z; ss[4 * h + 3] = sv.w;
+                }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const SymbolTable e = make_table(xs[k], ms[k], ss[k], s_tab, flags);
-                        uint32_t word;
-                        if (rans_push(state, e.start, e.freq, word)) scratch[wpos++] = word;
-                    }
+                for (int k = 0; k < 8; ++k) {
+                    const SymbolTable e = make_table(xs[k], ms[k], ss[k], s_tab, flags);
+                    uint32_t word;
+                    if (rans_push(state, e.start, e.freq, word)) scratch[wpos++] = word;
                 }
             } else {
                 for (int j = j_lo; j < j_hi; ++j) {
