@@ -203,10 +203,10 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     const int64_t my_blocks = len > 0 ? t_hi - t_lo + 1 : 0;
     const int64_t n_iter = warp_max_i64(my_blocks);
 
-    const uint32_t* wp = packed + wbeg;
     uint32_t wrem = too_long ? 0u : (uint32_t)wcount;
+    const uint32_t* wptr = packed + wbeg + wrem;   // one past the word held in next_word
     uint64_t state = live ? states[stream] : kRansL;
-    uint32_t next_word = wrem ? __ldg(wp + (wrem - 1)) : 0u;
+    uint32_t next_word = wrem ? __ldg(wptr - 1) : 0u;
     int32_t flags = too_long ? ST_TOO_LONG : 0;
 
     // this lane's rows in the two buffers
@@ -259,7 +259,8 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                     if (wrem) {
                         state = (state << 32) | next_word;
                         --wrem;
-                        if (wrem) next_word = __ldg(wp + (wrem - 1));
+                        --wptr;
+                        if (wrem) next_word = __ldg(wptr - 1);
                     } else {
                         flags |= ST_UNDERRUN;
                     }
