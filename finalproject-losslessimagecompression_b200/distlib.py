@@ -5,9 +5,9 @@ log_prob is the *ideal* code length the coder's real cost is compared against
 
 On CUDA tensors without autograd both run as one fused kernel each (csrc/logistic_prob.cu:
 flic_dlogistic_log_prob / flic_dlogistic_sample), with the per-image
-reduction of IDFlows.log_likelihood available in the same pass (log_prob_sums).  When a
-gradient is needed (training, which is outside the coding path) or the tensors live on the
-CPU (host-logic tests against the reference's goldens) the same formulas run as torch ops.
+reduction of IDFlows.log_likelihood available in the same pass (log_prob_sums).  Only when a
+gradient is needed (training, which is outside the coding path) does the same formula run as
+differentiable torch ops; without autograd there is no CPU implementation -- CPU tensors raise.
 """
 import ctypes as C
 from copy import deepcopy
@@ -25,10 +25,20 @@ class NNDistribution(Register):
     pass
 
 
+def _needs_autograd(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
 def _fused_ok(*tensors) -> bool:
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+    """True: run the fused kernel.  False: autograd is needed, use the differentiable torch formula.
+    Raises for inputs the kernel cannot take (CPU tensors, other dtypes): there is no CPU fallback."""
+    if _needs_autograd(*tensors):
         return False
-    return all(t.is_cuda and t.dtype == torch.float32 for t in tensors)
+    if not all(t.is_cuda for t in tensors):
+        raise _lib.FlicError("DLogistic needs CUDA tensors (no CPU implementation outside autograd)")
+    if not all(t.dtype == torch.float32 for t in tensors):
+        raise TypeError("DLogistic expects float32 tensors")
+    return True
 
 
 def _stream_ptr(dev):
@@ -54,8 +64,11 @@ class DLogistic(nn.Module):
         return up + torch.log(1 - torch.exp(dn - up) + eps)   # distlib.py:52-55
 
     def log_prob(self, x, mean, logscale, nbits=8, eps=1e-8):
-        if not (_fused_ok(x, mean, logscale) and x.shape == mean.shape == logscale.shape and x.numel() > 0):
+        if not _fused_ok(x, mean, logscale):
             return self._log_prob_torch(x, mean, logscale, nbits, eps)
+        x, mean, logscale = torch.broadcast_tensors(x, mean, logscale)
+        if x.numel() == 0:
+            return torch.empty_like(x)
         xv, mv, lv = x.contiguous(), mean.contiguous(), logscale.contiguous()
         out = torch.empty_like(xv)
         with torch.cuda.device(xv.device):
@@ -67,8 +80,11 @@ class DLogistic(nn.Module):
     def log_prob_sums(self, x, mean, logscale, nbits=8, eps=1e-8):
         """sum of log_prob over every dimension but the first, (B,) float32: the reduction of
         IDFlows.log_likelihood (flows.py:165-167) fused into the evaluation."""
-        if not (_fused_ok(x, mean, logscale) and x.shape == mean.shape == logscale.shape and x.numel() > 0):
+        if not _fused_ok(x, mean, logscale):
             return self._log_prob_torch(x, mean, logscale, nbits, eps).flatten(1).sum(1)
+        x, mean, logscale = torch.broadcast_tensors(x, mean, logscale)
+        if x.numel() == 0:
+            return torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
         xv, mv, lv = x.contiguous(), mean.contiguous(), logscale.contiguous()
         b = xv.shape[0]
         out = torch.empty(b, dtype=torch.float32, device=xv.device)

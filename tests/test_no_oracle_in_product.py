@@ -38,6 +38,11 @@ def test_product_has_no_cpu_fallback():
     img = torch.zeros(1, 4, 2, 2)
     with pytest.raises(_lib.FlicError):
         couplelib.couple_add_round(img, img[:, 3:], 3, 1)
+    from flic_b200.distlib import DLogistic
+    with pytest.raises(_lib.FlicError):
+        DLogistic().log_prob(img, img, img)            # only the autograd (training) path runs as torch ops
+    with pytest.raises(_lib.FlicError):
+        DLogistic().sample(img, img)
     with pytest.raises(_lib.FlicError):
         extenddim.squeeze(img, 2, 1)
     with pytest.raises(_lib.FlicError):
