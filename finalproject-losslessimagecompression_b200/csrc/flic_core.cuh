@@ -558,8 +558,8 @@ FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
     int P = mi - 1024, Q = 16776192 - mi;
     P = P < 2 ? 2 : P;
     Q = Q < 2 ? 2 : Q;
-    // A sig(u0) - mod: -1024 unless a tail clamp moved P or Q (exact in integers)
-    const int off = P - Q + 16776192 - 2 * mi;
+    // A sig(u0) - mod is -1024 unless a tail clamp moved P or Q, i.e. for 2 x 1026 of the 2^24
+    // values of mod; there the guess is just less sharp (the bracket search takes over)
     const float Pf = (float)P, Qf = (float)Q;
 #if defined(__CUDA_ARCH__)
     float lp, lq;   // P, Q >= 2 are normal floats: the flush-to-zero forms skip the subnormal fix-ups
@@ -569,7 +569,7 @@ FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
 #else
     const float u0 = (log2f(Pf) - log2f(Qf)) * 0.693147181f;
 #endif
-    const float h = ffma(c, u0, (m - (float)lower) + (float)off);
+    const float h = ffma(c, u0, (m - (float)lower) - 1024.0f);
     const float dh = ffma(Pf * (1.0f / 16775168.0f), Qf, c);
 #if defined(__CUDA_ARCH__)
     float rdh;
