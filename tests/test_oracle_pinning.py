@@ -156,8 +156,10 @@ def test_device_header_on_host_matches_oracle(oracle, host_harness, kind):
     assert np.array_equal(out, x) and end.value == 1 << 32
     # the guess-then-verify search needs ~2 exact CDF evaluations per symbol (reference: 13-14);
     # `edges` pins every symbol to the first/last bins of its window (probability ~1e-7 each under
-    # the model), where the one-step Newton guess is least converged and the bracket search works
-    assert evals.value / n < (4.5 if kind == "edges" else 2.01)
+    # the model): their `mod` falls in the 2 x 1026 values where the guess deliberately skips the
+    # tail correction of its Newton step (5 instructions per symbol saved on everything else), so
+    # the bracket search does the work there -- still half the reference's 13-14 evaluations
+    assert evals.value / n < (7.0 if kind == "edges" else 2.01)
     out2 = np.zeros(n, np.float32)
     assert H.hh_decode_fast(_p(words, C.c_uint32), nw.value, state.value, _p(mean, C.c_float), _p(scale, C.c_float),
                             n, _p(out2, C.c_float), C.byref(end)) == 0
