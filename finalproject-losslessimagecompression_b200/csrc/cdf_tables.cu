@@ -11,6 +11,10 @@
 
 namespace flic {
 
+// VEC = 4: each thread takes four consecutive symbols with 16-byte loads and stores (arrays 16-byte
+// aligned); the four evaluations are independent, which gives the scheduler eight FP64 chains per
+// thread.  VEC = 1: any alignment, and the tail of a vector launch.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                   const float* __restrict__ scale, int64_t n, uint32_t* __restrict__ start,
@@ -20,18 +24,46 @@ cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
     int32_t flags = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // software pipeline: the next symbol's parameters are in flight while this one is evaluated,
-    // so HBM latency never sits in front of the arithmetic
-    float xv = __ldg(x + i), mv = __ldg(mean + i), sv = __ldg(scale + i);
-    for (; i < n; i += stride) {
-        const int64_t nx = i + stride;
-        float xn = 0.0f, mn = 0.0f, sn = 1.0f;
-        if (nx < n) { xn = __ldg(x + nx); mn = __ldg(mean + nx); sn = __ldg(scale + nx); }
-        const SymbolTable t = make_table(xv, mv, sv, s_tab, flags);
-        start[i] = t.start;
-        freq[i] = t.freq;
-        xv = xn; mv = mn; sv = sn;
+    const int64_t groups = n / VEC;
+    if (i < groups) {
+        // software pipeline: the next group's parameters are in flight while this one is evaluated,
+        // so HBM latency never sits in front of the arithmetic
+        float xv[VEC], mv[VEC], sv[VEC];
+        auto load = [&](int64_t g, float* a, float* b, float* c) {
+            if (VEC == 4) {
+                const float4 p = __ldg(reinterpret_cast<const float4*>(x) + g);
+                const float4 q = __ldg(reinterpret_cast<const float4*>(mean) + g);
+                const float4 r = __ldg(reinterpret_cast<const float4*>(scale) + g);
+                a[0] = p.x; a[1] = p.y; a[2] = p.z; a[3] = p.w;
+                b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
+                c[0] = r.x; c[1] = r.y; c[2] = r.z; c[3] = r.w;
+            } else {
+                a[0] = __ldg(x + g); b[0] = __ldg(mean + g); c[0] = __ldg(scale + g);
+            }
+        };
+        load(i, xv, mv, sv);
+        for (; i < groups; i += stride) {
+            float xn[VEC], mn[VEC], sn[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { xn[k] = 0.0f; mn[k] = 0.0f; sn[k] = 1.0f; }
+            if (i + stride < groups) load(i + stride, xn, mn, sn);
+            uint32_t st[VEC], fr[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const SymbolTable t = make_table(xv[k], mv[k], sv[k], s_tab, flags);
+                st[k] = t.start;
+                fr[k] = t.freq;
+            }
+            if (VEC == 4) {
+                reinterpret_cast<uint4*>(start)[i] = make_uint4(st[0], st[1], st[2], st[3]);
+                reinterpret_cast<uint4*>(freq)[i] = make_uint4(fr[0], fr[1], fr[2], fr[3]);
+            } else {
+                start[i] = st[0];
+                freq[i] = fr[0];
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { xv[k] = xn[k]; mv[k] = mn[k]; sv[k] = sn[k]; }
+        }
     }
     if (flags) atomicOr(status_word, flags);
 }
@@ -168,10 +200,21 @@ cudaError_t launch_cdf_tables(const float* x, const float* mean, const float* sc
     if (n <= 0) return cudaSuccess;
     const int sms = sm_count();
     const int threads = 256;
-    int64_t blocks = (n + threads - 1) / threads;
     const int64_t cap = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
-    if (blocks > cap) blocks = cap;
-    cdf_tables_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, mean, scale, n, start, freq, status_word);
+    const bool aligned = (((uintptr_t)x | (uintptr_t)mean | (uintptr_t)scale | (uintptr_t)start | (uintptr_t)freq) & 15) == 0;
+    const int64_t n4 = aligned ? n / 4 * 4 : 0;
+    if (n4 > 0) {
+        int64_t blocks = (n4 / 4 + threads - 1) / threads;
+        if (blocks > cap) blocks = cap;
+        cdf_tables_kernel<4><<<(unsigned)blocks, threads, 0, stream>>>(x, mean, scale, n4, start, freq, status_word);
+    }
+    if (n > n4) {   // unaligned arrays, or the last 1-3 symbols
+        const int64_t m = n - n4;
+        int64_t blocks = (m + threads - 1) / threads;
+        if (blocks > cap) blocks = cap;
+        cdf_tables_kernel<1><<<(unsigned)blocks, threads, 0, stream>>>(x + n4, mean + n4, scale + n4, m, start + n4,
+                                                                       freq + n4, status_word);
+    }
     return cudaGetLastError();
 }
 
