@@ -19,8 +19,8 @@ __global__ void __launch_bounds__(256)
 cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                   const float* __restrict__ scale, int64_t n, uint32_t* __restrict__ start,
                   uint32_t* __restrict__ freq, int32_t* __restrict__ status_word) {
-    __shared__ uint64_t s_tab[32];
-    stage_exp_table(s_tab);
+    __shared__ __align__(256) uint64_t s_tab[32];
+    const ExpTab tab = stage_exp_table(s_tab);
     int32_t flags = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,7 +50,7 @@ cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
             uint32_t st[VEC], fr[VEC];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                const SymbolTable t = make_table(xv[k], mv[k], sv[k], s_tab, flags);
+                const SymbolTable t = make_table(xv[k], mv[k], sv[k], tab, flags);
                 st[k] = t.start;
                 fr[k] = t.freq;
             }
@@ -72,22 +72,22 @@ cdf_tables_kernel(const float* __restrict__ x, const float* __restrict__ mean,
 // libm over the whole reachable domain.
 __global__ void __launch_bounds__(256)
 debug_expf_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
-    __shared__ uint64_t s_tab[32];
-    stage_exp_table(s_tab);
+    __shared__ __align__(256) uint64_t s_tab[32];
+    const ExpTab tab = stage_exp_table(s_tab);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        y[i] = expf_glibc(x[i], s_tab);
+        y[i] = expf_glibc(x[i], tab);
 }
 
 // Diagnostic: part1 as a function of the float argument alone (the quotient stage replaced by a
 // plain widening), for the exhaustive sweep against the reference arithmetic.
 __global__ void __launch_bounds__(256)
 debug_part1_kernel(const float* __restrict__ arg, int32_t* __restrict__ y, int64_t n) {
-    __shared__ uint64_t s_tab[32];
-    stage_exp_table(s_tab);
+    __shared__ __align__(256) uint64_t s_tab[32];
+    const ExpTab tab = stage_exp_table(s_tab);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        y[i] = part1_from_arg(arg_from_quotient((double)arg[i]), s_tab);
+        y[i] = part1_from_arg(arg_from_quotient((double)arg[i]), tab);
 }
 
 cudaError_t launch_debug_part1(const float* arg, int32_t* y, int64_t n, cudaStream_t stream) {

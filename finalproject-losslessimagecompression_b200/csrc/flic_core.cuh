@@ -277,8 +277,27 @@ FLIC_HD double clamp_mag128(double q) {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,   \
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull
 
-// `tab` points at the 32-entry table: shared memory on the device (each lane indexes its own
-// entry, so constant memory would serialise), a static array on the host.
+// `tab` names the 32-entry table: on the device the shared-space byte address of a 256-byte
+// aligned copy (each lane indexes its own entry, so constant memory would serialise; a 32-bit
+// shared address costs one LOP3 per lookup where a generic pointer costs the shared-window base
+// -- S2R + LEA -- per use), a static array on the host.
+#if defined(__CUDACC__)
+typedef uint32_t ExpTab;
+#else
+typedef const uint64_t* ExpTab;
+#endif
+FLIC_HD uint64_t exp_tab_entry(ExpTab tab, uint32_t ki) {
+#if defined(__CUDA_ARCH__)
+    uint64_t v;
+    asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(tab | ((ki << 3) & 0xf8u)));
+    return v;
+#elif defined(__CUDACC__)
+    (void)tab; (void)ki;
+    return 0;   // nvcc's host pass only; the product never evaluates the coder on the host
+#else
+    return tab[ki & 31];
+#endif
+}
 //
 // exp_core(xd) is the double-precision body of glibc's expf for xd = (double)x: it returns the
 // product y * s whose conversion to float is the function's result.  Valid (no exponent
@@ -287,19 +306,30 @@ FLIC_HD double clamp_mag128(double q) {
 // sweeps every float |x| <= 104 against the host libm: equal everywhere except two inputs deep
 // inside part1's saturated range, where the host itself departs from the published algorithm.
 // `neg` evaluates exp(-xd): (-InvLn2N) * xd is bit-identical to InvLn2N * (-xd).
-FLIC_HD double exp_core(double xd, const uint64_t* tab, bool neg) {
+#if defined(__CUDACC__)
+// InvLn2N, C0, C1, C2 of exp_core(): their low words are not zero, so they cannot be immediates;
+// from constant memory two of them arrive per uniform load instead of costing two moves each
+// every time register pressure makes the compiler rebuild them.
+static __constant__ double c_expk[4] = {0x1.71547652b82fep+0 * 32.0, 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0,
+                                        0x1.ebfce50fac4f3p-3 / 32.0 / 32.0, 0x1.62e42ff0c52d6p-1 / 32.0};
+#endif
+FLIC_HD double exp_core(double xd, ExpTab tab, bool neg) {
+#if defined(__CUDA_ARCH__)
+    const double InvLn2N = c_expk[0], C0 = c_expk[1], C1 = c_expk[2], C2 = c_expk[3];
+#else
     const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
-    const double Shift = 0x1.8p+52;
     const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0;
     const double C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0;
     const double C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+#endif
+    const double Shift = 0x1.8p+52;
     const double z = dmul(neg ? -InvLn2N : InvLn2N, xd);
     double kd = dadd(z, Shift);
     const uint32_t ki = f64_lo(kd);          // k mod 2^32 sits in the low mantissa bits
     kd = dsub(kd, Shift);
     const double r = dsub(z, kd);
     // T[k % 32] + (k << 47): the shift only reaches the high word (47 - 32 = 15)
-    const uint64_t tv = tab[ki & 31];
+    const uint64_t tv = exp_tab_entry(tab, ki);
     const double s = f64_from_words((uint32_t)(tv >> 32) + (ki << 15), (uint32_t)tv);
     // glibc evaluates (C0 r + C1) r^2 + (C2 r + 1); Horner's form has one operation less and
     // differs from it by an ulp or two of the double -- which could change the float result only
@@ -319,7 +349,7 @@ FLIC_HD double exp_core(double xd, const uint64_t* tab, bool neg) {
 // half the smallest subnormal, the very definition of glibc's underflow threshold), and the
 // results in between are the main path's anyway.  NaN is mapped to the lower clamp.
 // The coder itself uses exp_core() directly (part1_at); this wrapper exists for the sweeps.
-FLIC_HD float expf_glibc(float x, const uint64_t* tab) {  // x by value: clamped below
+FLIC_HD float expf_glibc(float x, ExpTab tab) {  // x by value: clamped below
     x = fminf(fmaxf(x, -104.0f), 89.0f);
     return d2f(exp_core((double)x, tab, false));
 }
@@ -346,13 +376,35 @@ struct SymbolModel {
 // every window index stays below 2^23 and the float arithmetic of rans.pyx:33 (x - lower) is
 // exact (8-bit image latents are within a few units of zero).  NaN fails every comparison.
 FLIC_HD bool params_ok(float mean, float scale) {
-    return (fabsf(mean) <= 16384.0f) && (fabsf(scale) < INFINITY) && (scale != 0.0f);
+    return (fabsf(mean) <= 16384.0f) && (scale < INFINITY) && (scale > 0.0f);
 }
-// Status bits for parameters that are not ok (slow path only).
+// Status bits for parameters that are not ok (slow path only).  A negative scale makes part1
+// decrease in s (freq <= 0: the reference divides by zero or corrupts the stream); it is
+// reported with the non-finite ones.
 FLIC_HD int32_t param_flags(float mean, float scale) {
     int32_t f = 0;
     if (scale == 0.0f) f |= ST_ZERO_SCALE;
-    if (!(fabsf(mean) <= 16384.0f) || !(fabsf(scale) < INFINITY)) f |= ST_NONFINITE;
+    if (!(fabsf(mean) <= 16384.0f) || !(scale < INFINITY) || scale < 0.0f) f |= ST_NONFINITE;
+    return f;
+}
+
+// The same test for a whole stream at three integer instructions per symbol: running unsigned
+// maxima of bits(scale) - 1 (zero wraps to 0xffffffff, negative values and NaN / inf are
+// >= 0x7f7fffff) and of bits(|mean|) (16384.0f is 0x46800000; NaN is above it).  The hot loops
+// note every symbol and turn the maxima into status bits once per stream.
+struct ParamGuard {
+    uint32_t smax, mmax;
+};
+FLIC_HD ParamGuard guard_init() { ParamGuard g; g.smax = 0u; g.mmax = 0u; return g; }
+FLIC_HD void guard_note(ParamGuard& g, float mean, float scale) {
+    const uint32_t sb = f32_bits(scale) - 1u, mb = f32_bits(mean) & 0x7fffffffu;
+    g.smax = sb > g.smax ? sb : g.smax;
+    g.mmax = mb > g.mmax ? mb : g.mmax;
+}
+FLIC_HD int32_t guard_flags(const ParamGuard& g) {
+    int32_t f = 0;
+    if (g.smax >= 0x7f7fffffu) f |= (g.smax == 0xffffffffu || g.smax == 0x7fffffffu) ? ST_ZERO_SCALE : ST_NONFINITE;
+    if (g.mmax > 0x46800000u) f |= ST_NONFINITE;
     return f;
 }
 
@@ -412,7 +464,7 @@ FLIC_HD double div_by_scale(double a, const SymbolModel& m) {
 // Everything after the argument: arg is (double)(float)arg_f with |arg| <= 128 (or <= 128.001 from
 // the FP64-pipe rounding).  A pure function of a 32-bit float, so it is swept exhaustively
 // against the reference arithmetic on the GPU (tests/test_gpu_flow.py, flic_debug_part1).
-FLIC_HD int part1_from_arg(double arg, const uint64_t* tab) {
+FLIC_HD int part1_from_arg(double arg, ExpTab tab) {
 #if FLIC_E_XU
     const double e = (double)fminf(d2f(exp_core(arg, tab, true)), 3.402823466e+38f);
 #else
@@ -436,7 +488,7 @@ FLIC_HD double arg_from_quotient(double q) {
 #endif
 }
 
-FLIC_HD int part1_at(double a, const SymbolModel& m, const uint64_t* tab) {
+FLIC_HD int part1_at(double a, const SymbolModel& m, ExpTab tab) {
     const double t4 = dsub(a, m.mean_d);
     return part1_from_arg(arg_from_quotient(div_by_scale(t4, m)), tab);
 }
@@ -451,13 +503,13 @@ FLIC_HD double half_bin_point(int s) {
 // CDF(s/256) for integer symbol s: part1 + part2, part2 = round((xq - lower_f) * 256) + 1
 // = s - lower + 1 exactly when |s| and |lower| are below 2^24 (both floats exact, difference
 // exact).
-FLIC_HD int cdf_at(int s, const SymbolModel& m, const uint64_t* tab) {
+FLIC_HD int cdf_at(int s, const SymbolModel& m, ExpTab tab) {
     return part1_at(half_bin_point(s), m, tab) + (s - m.lower + 1);
 }
 
 // CDF(s-1) and CDF(s) together: the (start, end) pair of symbol s (rans.pyx:52-53, :106-107).
 // The two evaluations are independent and interleave in the instruction stream.
-FLIC_HD void cdf_pair(int s, const SymbolModel& m, const uint64_t* tab, int& c_lo, int& c_hi) {
+FLIC_HD void cdf_pair(int s, const SymbolModel& m, ExpTab tab, int& c_lo, int& c_hi) {
     const double a_hi = half_bin_point(s);
     const double a_lo = dsub(a_hi, 0.00390625);  // exact
     c_hi = part1_at(a_hi, m, tab) + (s - m.lower + 1);
@@ -475,7 +527,7 @@ struct SymbolTable {
 // part2 is plain integer arithmetic.  Anything else makes the reference silently emit an
 // undecodable stream; here the stream is flagged and a harmless entry keeps
 // the coder alive.
-FLIC_HD SymbolTable make_table(float x, float mean, float scale, const uint64_t* tab, int32_t& flags) {
+FLIC_HD SymbolTable make_table(float x, float mean, float scale, ExpTab tab, int32_t& flags) {
     const SymbolModel m = make_model(mean, scale);
     const float xs = x * 256.0f;
     const int s = f2i_rz(xs);
@@ -488,6 +540,24 @@ FLIC_HD SymbolTable make_table(float x, float mean, float scale, const uint64_t*
     }
     int c0, c1;
     cdf_pair(s, m, tab, c0, c1);
+    t.start = (uint32_t)c0;
+    t.freq = (uint32_t)(c1 - c0);
+    return t;
+}
+
+// make_table() for the hot loops: parameters are noted in `guard` instead of being tested per
+// symbol, and the entry is computed unconditionally -- for a symbol or parameters that are not
+// codable it is meaningless but harmless (no trap, no unbounded loop, at most one word per
+// symbol either way) and the stream is flagged.
+FLIC_HD SymbolTable make_table_lean(float x, float mean, float scale, ExpTab tab, ParamGuard& guard, int32_t& flags) {
+    const SymbolModel m = make_model(mean, scale);
+    guard_note(guard, mean, scale);
+    const float xs = x * 256.0f;
+    const int s = f2i_rz(xs);
+    if (!(((float)s == xs) && ((uint32_t)(s - m.lower) < (uint32_t)kWindow))) flags |= ST_OUT_OF_WINDOW;
+    int c0, c1;
+    cdf_pair(s, m, tab, c0, c1);
+    SymbolTable t;
     t.start = (uint32_t)c0;
     t.freq = (uint32_t)(c1 - c0);
     return t;
@@ -542,6 +612,16 @@ FLIC_HD void rans_pop(uint64_t& state, uint32_t start, uint32_t freq) {
     state = (state >> 24) * (uint64_t)freq + (state & kProbMask) - (uint64_t)start;
 }
 
+// The same on the state's two words: x = state >> 24 is 40 bits (xh:xl), mod - start is in
+// [0, freq), and the new state is x freq + (mod - start) < 2^64.
+FLIC_HD void rans_pop32(uint32_t& hi, uint32_t& lo, uint32_t start, uint32_t freq) {
+    const uint32_t xl = (hi << 8) | (lo >> 24), xh = hi >> 24;
+    const uint32_t d = (lo & kProbMask) - start;
+    const uint64_t p = (uint64_t)xl * freq + d;
+    hi = (uint32_t)(p >> 32) + xh * freq;
+    lo = (uint32_t)p;
+}
+
 // ---- decoder symbol search ----------------------------------------------------------------------
 // First guess for "smallest s with CDF(s) > mod" from the continuous model
 //   g(s) = A sigmoid((s + 0.5 - 256 mean) / (256 scale)) + (s - lower + 1),  A = 16775168
@@ -555,7 +635,8 @@ FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
     const float m = mean * 256.0f;
     const float c = scale * 256.0f;
     const int mi = (int)mod;
-    int P = mi - 1024, Q = 16776192 - mi;
+    // Q = A + 1024 - mod = (mod ^ 0xffffff) - 1023 for mod < 2^24 (no constant register needed)
+    int P = mi - 1024, Q = (int)(mod ^ 0xffffffu) - 1023;
     P = P < 2 ? 2 : P;
     Q = Q < 2 ? 2 : Q;
     // A sig(u0) - mod is -1024 unless a tail clamp moved P or Q, i.e. for 2 x 1026 of the 2^24
@@ -648,7 +729,7 @@ FLIC_HD void search_feed(SearchState& st, int c, uint32_t mod) {
 
 // One symbol.  Returns the integer grid index; updates state.
 FLIC_HD int decode_symbol(uint64_t& state, float mean, float scale,
-                                             const uint64_t* s_tab, int32_t& flags) {
+                                             ExpTab s_tab, int32_t& flags) {
     const uint32_t mod = (uint32_t)state & kProbMask;
     const SymbolModel m = make_model(mean, scale);
     if (!params_ok(mean, scale)) flags |= param_flags(mean, scale);
@@ -677,6 +758,66 @@ FLIC_HD int decode_symbol(uint64_t& state, float mean, float scale,
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
     }
     rans_pop(state, (uint32_t)c_lo, (uint32_t)(c_hi - c_lo));
+    return s;
+}
+
+// ---- the decoder's hot path --------------------------------------------------------------------
+// decode_symbol() split where the probabilities split: the guess is right for all but a few
+// symbols per million, so the bracket search is a function of its own (not inlined on the
+// device: its registers and code stay out of the unrolled loop), parameters are noted in a
+// ParamGuard instead of being tested, and the state is the (hi, lo) word pair the word pull
+// works on.
+struct SymbolHit {
+    int s, c_lo, c_hi;
+};
+
+#ifndef FLIC_SEARCH_NOINLINE
+#define FLIC_SEARCH_NOINLINE 1
+#endif
+#if defined(__CUDA_ARCH__) && FLIC_SEARCH_NOINLINE
+__device__ __noinline__
+#elif defined(__CUDA_ARCH__)
+__device__ __forceinline__
+#else
+static inline
+#endif
+SymbolHit decode_symbol_search(uint32_t mod, float mean, float scale, ExpTab tab, int g, int c_lo, int c_hi) {
+    const SymbolModel m = make_model(mean, scale);
+    SearchState st;
+    st.lo = m.lower - 1; st.hi = m.lower + kWindow;
+    st.c_lo = -1; st.c_hi = -1; st.step = 2; st.done = false;
+    if (c_hi <= (int)mod) {  // answer is right of g
+        st.lo = g; st.c_lo = c_hi;
+        st.probe = g + 1 < st.hi ? g + 1 : st.hi;
+    } else {                 // c_lo > mod and g - 1 >= lower: answer is at or left of g - 1
+        st.hi = g - 1; st.c_hi = c_lo;
+        st.probe = g - 2 > st.lo ? g - 2 : st.lo;
+    }
+    while (!st.done) {
+        const int c = cdf_at(st.probe, m, tab);
+        search_feed(st, c, mod);
+    }
+    SymbolHit h;
+    h.s = st.hi; h.c_lo = st.c_lo; h.c_hi = st.c_hi;
+    return h;
+}
+
+FLIC_HD int decode_symbol_lean(uint32_t& hi, uint32_t& lo, float mean, float scale, ExpTab tab,
+                               ParamGuard& guard, int32_t& flags) {
+    const uint32_t mod = lo & kProbMask;
+    const SymbolModel m = make_model(mean, scale);
+    guard_note(guard, mean, scale);
+    const int g = guess_symbol(mod, mean, scale, m.lower);
+    int c_lo, c_hi;
+    cdf_pair(g, m, tab, c_lo, c_hi);
+    int s = g;
+    const bool left_ok = (g == m.lower) || (c_lo <= (int)mod);  // window's left edge is virtual
+    if (!(left_ok && c_hi > (int)mod)) {
+        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
+        s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
+        if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
+    }
+    rans_pop32(hi, lo, (uint32_t)c_lo, (uint32_t)(c_hi - c_lo));
     return s;
 }
 

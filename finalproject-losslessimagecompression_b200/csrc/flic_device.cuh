@@ -8,9 +8,15 @@ namespace flic {
 // memory once per CTA (lanes index it divergently, which constant memory would serialise).
 static __constant__ uint64_t c_exp2f_tab[32] = {FLIC_EXP2F_TABLE};
 
-__device__ __forceinline__ void stage_exp_table(uint64_t* s_tab) {
+// s_tab must be declared __align__(256) (exp_tab_entry() ORs the entry offset into the address).
+// Returns the table's shared-space address, made opaque so that it stays in one register instead
+// of being recomputed from the shared-window base at every lookup.
+__device__ __forceinline__ ExpTab stage_exp_table(uint64_t* s_tab) {
     if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
     __syncthreads();
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(s_tab);
+    asm volatile("" : "+r"(a));
+    return a;
 }
 
 // CTA-wide barrier that may be reached from different code paths of a warp-specialised kernel

@@ -50,9 +50,9 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
                    const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                    int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
                    int32_t* __restrict__ status, int check_end) {
-    __shared__ uint64_t s_tab[32];
+    __shared__ __align__(256) uint64_t s_tab[32];
     __shared__ float2 s_tile[WARPS][2][kLanes][kDecTile + 1];
-    stage_exp_table(s_tab);
+    const ExpTab tab = stage_exp_table(s_tab);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -123,7 +123,7 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
                     }
                 }
                 const float2 ms = tile[lane][j];
-                const int s = decode_symbol(state, ms.x, ms.y, s_tab, flags);
+                const int s = decode_symbol(state, ms.x, ms.y, tab, flags);
                 tile[lane][j].x = (float)s * 0.00390625f;  // s / 256., exact
             }
         }
@@ -172,6 +172,12 @@ __device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
+// Bookkeeping is per lane and 32-bit: a lane's blocks are numbered q = 0 (the stream's last
+// symbols) .. nb - 1 (its first); only block 0 and block nb - 1 can be partial, every other one is
+// a whole 32-byte sector per array, so the loop carries three running pointers and a counter
+// instead of 64-bit symbol indices.  The word pull is predicated (select + conditional load, no
+// divergent branch): with 32 lanes, some lane renormalises at nearly every symbol, and a branch
+// would make the whole warp walk its body each time.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? FLIC_DEC_MIN_BLOCKS : 16)
 rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ word_offsets,
@@ -179,10 +185,10 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                         const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                         int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
                         int32_t* __restrict__ status, int check_end, int shift) {
-    __shared__ uint64_t s_tab[32];
-    __shared__ __align__(16) float s_mean[WARPS][2][kLanes][kBlkPitch];
-    __shared__ __align__(16) float s_scale[WARPS][2][kLanes][kBlkPitch];
-    stage_exp_table(s_tab);
+    __shared__ __align__(256) uint64_t s_tab[32];
+    // [buffer][mean, scale][lane][kBlkPitch]
+    __shared__ __align__(16) float s_par[WARPS][2][2][kLanes][kBlkPitch];
+    const ExpTab tab = stage_exp_table(s_tab);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -195,82 +201,95 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     int64_t len = live ? offsets[stream + 1] - beg : 0;
     const int64_t wbeg = live ? word_offsets[stream] : 0;
     const int64_t wcount = live ? word_offsets[stream + 1] - wbeg : 0;
-    const bool too_long = wcount > 0xffffffffll;
+    // 32-bit counters: a single stream of 2^31 symbols (or words) is not supported
+    const bool too_long = wcount > 0x7fffffffll || len > 0x7fffffffll;
     if (too_long) len = 0;
     const int64_t end = beg + len;
-    // blocks of this lane, last to first: T_hi, T_hi - 1, ..., T_lo
     const int64_t t_hi = (end - 1 + shift) >> kBlkShift, t_lo = (beg + shift) >> kBlkShift;
-    const int64_t my_blocks = len > 0 ? t_hi - t_lo + 1 : 0;
-    const int64_t n_iter = warp_max_i64(my_blocks);
+    const int nb = len > 0 ? (int)(t_hi - t_lo + 1) : 0;
+    int n_iter = nb;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_iter = max(n_iter, __shfl_xor_sync(0xffffffffu, n_iter, d));
+    // symbols [j_head, kBlk) of block nb - 1 and [0, j_tail) of block 0 belong to the stream
+    const int j_head = (int)((beg + shift) & (kBlk - 1));
+    const int j_tail = (int)((end - 1 + shift) & (kBlk - 1)) + 1;
+    const int j_ends = j_head | (j_tail << 4);
 
-    uint32_t wrem = too_long ? 0u : (uint32_t)wcount;
-    const uint32_t* wptr = packed + wbeg + wrem;   // one past the word held in next_word
-    uint64_t state = live ? states[stream] : kRansL;
-    uint32_t next_word = wrem ? __ldg(wptr - 1) : 0u;
+    const uint32_t* const wbase = packed + wbeg;
+    int wrem = too_long ? 0 : (int)wcount;          // unread words; negative once the stream has under-run
+    const uint64_t st0 = live ? states[stream] : kRansL;
+    uint32_t hi = (uint32_t)(st0 >> 32), lo = (uint32_t)st0;
+    uint32_t next_word = wrem > 0 ? __ldg(wbase + (wrem - 1)) : 0u;
     int32_t flags = too_long ? ST_TOO_LONG : 0;
+    ParamGuard guard = guard_init();
 
-    // this lane's rows in the two buffers
-    float* const row_mean = s_mean[warp][0][lane];
-    float* const row_scale = s_scale[warp][0][lane];
-    constexpr int kBufStride = kLanes * kBlkPitch;
+    // element index of the first slot of block q is i_stage (while staging) / i_dec (while decoding);
+    // the three arrays share the phase `shift`, so one running index serves them all
+    int64_t i_stage = (t_hi << kBlkShift) - shift;
+    int64_t i_dec = i_stage;
+    float* const row = s_par[warp][0][0][lane];
+    constexpr int kArr = kLanes * kBlkPitch, kBuf = 2 * kArr;
 
-    // stage block number q (counted from the stream's end) into buffer q & 1
-    auto prefetch = [&](int64_t q) {
-        if (q < my_blocks) {
-            const int64_t i0 = ((t_hi - q) << kBlkShift) - shift;       // first symbol index of the block
-            float* dm = row_mean + (int)(q & 1) * kBufStride;
-            float* ds = row_scale + (int)(q & 1) * kBufStride;
-            if (i0 >= beg && i0 + kBlk <= end) {                // whole block inside the stream
-                cp_async_16(dm, mean + i0);
-                cp_async_16(ds, scale + i0);
+    auto stage = [&](int q) {   // (mean, scale) of block q -> buffer q & 1
+        if (q < nb) {
+            float* d = row + (q & 1) * kBuf;
+            const float* pm = mean + i_stage;
+            const float* ps = scale + i_stage;
+            const int jl = q == nb - 1 ? (j_ends & 15) : 0, jh = q == 0 ? (j_ends >> 4) : kBlk;
+            if (jl == 0 && jh == kBlk) {
+                cp_async_16(d, pm);
+                cp_async_16(d + kArr, ps);
                 if (kBlk == 8) {
-                    cp_async_16(dm + 4, mean + i0 + 4);
-                    cp_async_16(ds + 4, scale + i0 + 4);
+                    cp_async_16(d + 4, pm + 4);
+                    cp_async_16(d + kArr + 4, ps + 4);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < kBlk; ++j)
-                    if (i0 + j >= beg && i0 + j < end) {
-                        cp_async_f32(dm + j, mean + i0 + j);
-                        cp_async_f32(ds + j, scale + i0 + j);
+                    if (j >= jl && j < jh) {
+                        cp_async_f32(d + j, pm + j);
+                        cp_async_f32(d + kArr + j, ps + j);
                     }
             }
+            i_stage -= kBlk;
         }
         cp_async_commit();
     };
+    auto pull = [&]() {  // rans.pyx:87-89
+        const uint32_t hi0 = hi;                     // state < 2^32 iff the high word is zero
+        hi = hi0 == 0u ? lo : hi0;
+        lo = hi0 == 0u ? next_word : lo;
+        wrem -= hi0 == 0u ? 1 : 0;
+        // if (hi0 == 0 && wrem > 0) next_word = wbase[wrem - 1], as a predicated load (the address
+        // is formed unconditionally: one multiply-add against selects and moves under a predicate)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
+                     "setp.eq.u32 p, %1, 0;\n\t"
+                     "setp.gt.and.s32 p, %2, 0, p;\n\t"
+                     "mad.wide.s32 a, %2, 4, %3;\n\t"
+                     "@p ld.global.nc.u32 %0, [a+-4];\n\t}"
+                     : "+r"(next_word) : "r"(hi0), "r"(wrem), "l"(wbase));
+    };
 
-    if (n_iter > 0) prefetch(0);
-    for (int64_t q = 0; q < n_iter; ++q) {
+    if (n_iter > 0) stage(0);
+    for (int q = 0; q < n_iter; ++q) {
         if (q + 1 < n_iter) {
-            prefetch(q + 1);
+            stage(q + 1);
             cp_async_wait<1>();   // block q has landed; block q+1 may still be in flight
         } else {
             cp_async_wait<0>();
         }
         // each lane reads only what it copied itself: no warp barrier needed
-        if (q < my_blocks) {
-            const int64_t i0 = ((t_hi - q) << kBlkShift) - shift;
-            float* bm = row_mean + (int)(q & 1) * kBufStride;
-            const float* bs = row_scale + (int)(q & 1) * kBufStride;
-            const int j_lo = i0 >= beg ? 0 : (int)(beg - i0);
-            const int j_hi = i0 + kBlk <= end ? kBlk : (int)(end - i0);
-            auto pull = [&]() {  // rans.pyx:87-89
-                if (state < kRansL) {
-                    if (wrem) {
-                        state = (state << 32) | next_word;
-                        --wrem;
-                        --wptr;
-                        if (wrem) next_word = __ldg(wptr - 1);
-                    } else {
-                        flags |= ST_UNDERRUN;
-                    }
-                }
-            };
-            if (kBlk == 8 && j_lo == 0 && j_hi == kBlk) {
+        if (q < nb) {
+            float* bm = row + (q & 1) * kBuf;
+            const float* bs = bm + kArr;
+            float* px = x_out + i_dec;
+            const int jl = q == nb - 1 ? (j_ends & 15) : 0, jh = q == 0 ? (j_ends >> 4) : kBlk;
+            if (kBlk == 8 && jl == 0 && jh == kBlk) {
                 // whole block: parameters come out of shared memory as 16-byte vectors (the row
-                // pitch keeps those conflict-free), four symbols are decoded from registers, last
-                // first, and leave as one 16-byte store
-#pragma unroll 1
+                // pitch keeps those conflict-free), four symbols at a time are decoded from
+                // registers, last first; the upper four are parked in the (now free) upper half
+                // of the mean row so that the whole 32-byte sector is written at once
+#pragma unroll
                 for (int h = 1; h >= 0; --h) {
                     const float4 mv = *reinterpret_cast<const float4*>(bm + 4 * h);
                     const float4 sv = *reinterpret_cast<const float4*>(bs + 4 * h);
@@ -280,27 +299,29 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
 #pragma unroll
                     for (int k = 3; k >= 0; --k) {
                         pull();
-                        xo[k] = (float)decode_symbol(state, ms[k], ss[k], s_tab, flags) * 0.00390625f;  // s / 256., exact
+                        xo[k] = (float)decode_symbol_lean(hi, lo, ms[k], ss[k], tab, guard, flags) * 0.00390625f;  // s / 256., exact
                     }
                     const float4 o = make_float4(xo[0], xo[1], xo[2], xo[3]);
                     if (h == 1) {
-                        // parked in the (now free) upper half of the mean row, so that the whole
-                        // 32-byte sector is written at once
                         *reinterpret_cast<float4*>(bm + 4) = o;
                     } else {
-                        *reinterpret_cast<float4*>(x_out + i0) = o;
-                        *reinterpret_cast<float4*>(x_out + i0 + 4) = *reinterpret_cast<const float4*>(bm + 4);
+                        *reinterpret_cast<float4*>(px) = o;
+                        *reinterpret_cast<float4*>(px + 4) = *reinterpret_cast<const float4*>(bm + 4);
                     }
                 }
             } else {
-                for (int j = j_hi - 1; j >= j_lo; --j) {
+                for (int j = jh - 1; j >= jl; --j) {
                     pull();
-                    x_out[i0 + j] = (float)decode_symbol(state, bm[j], bs[j], s_tab, flags) * 0.00390625f;
+                    px[j] = (float)decode_symbol_lean(hi, lo, bm[j], bs[j], tab, guard, flags) * 0.00390625f;
                 }
             }
+            i_dec -= kBlk;
         }
     }
     if (live) {
+        flags |= guard_flags(guard);
+        if (wrem < 0) flags |= ST_UNDERRUN;
+        const uint64_t state = ((uint64_t)hi << 32) | lo;
         if (check_end && !too_long && (state != kRansL || wrem != 0)) flags |= ST_BAD_END_STATE;
         end_states[stream] = state;
         status[stream] = flags;

@@ -51,7 +51,7 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                    int64_t n_streams, const uint64_t* __restrict__ init_states,
                    uint32_t* __restrict__ scratch, int64_t* __restrict__ counts,
                    uint64_t* __restrict__ states, int32_t* __restrict__ status) {
-    __shared__ uint64_t s_tab[32];
+    __shared__ __align__(256) uint64_t s_tab[32];
     __shared__ uint2 s_tile[2][kLanes][kTile + 1];
     __shared__ int64_t s_beg[kLanes], s_len[kLanes];
     __shared__ int32_t s_flags[kLanes];
@@ -72,7 +72,7 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
         const int64_t mx = warp_max_i64(len);
         if (lane == 0) s_max_len = mx;
     }
-    stage_exp_table(s_tab);  // CTA barrier inside
+    const ExpTab tab = stage_exp_table(s_tab);  // CTA barrier inside
     const int64_t n_tiles = (s_max_len + kTile - 1) / kTile;
 
     if (warp > 0) {
@@ -103,7 +103,7 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                     const int r = r0 + q;
                     if (on[q]) {
                         int32_t f = 0;
-                        const SymbolTable e = make_table(xv[q], mv[q], sv[q], s_tab, f);
+                        const SymbolTable e = make_table(xv[q], mv[q], sv[q], tab, f);
                         tile[r][lane] = make_uint2(e.start, e.freq);
                         if (f) atomicOr(&s_flags[r], f);  // rare
                     }
@@ -174,16 +174,21 @@ __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_sr
 // less DRAM over-fetch -- the more lanes stream concurrently, the more of the 64-byte DRAM bursts'
 // second halves are evicted from L2 before their lane asks for them (ncu: 23.5 / 22.0 / 20.4 GB
 // read at 9 / 7 / 6 CTAs for 19.3 GB of inputs).
+// Bookkeeping is 32-bit and per lane as in the decoder (rans_decode.cu): blocks q = 0 .. nb - 1,
+// only the first and the last can be partial, one running element index for the three arrays.
+#ifndef FLIC_ENC_MIN_BLOCKS
+#define FLIC_ENC_MIN_BLOCKS 7
+#endif
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 7)
+__global__ void __launch_bounds__(WARPS * 32, FLIC_ENC_MIN_BLOCKS)
 rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                         const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                         int64_t n_streams, const uint64_t* __restrict__ init_states,
                         uint32_t* __restrict__ scratch, int64_t* __restrict__ counts,
                         uint64_t* __restrict__ states, int32_t* __restrict__ status, int shift) {
-    __shared__ uint64_t s_tab[32];
+    __shared__ __align__(256) uint64_t s_tab[32];
     __shared__ __align__(16) float s_in[WARPS][2][3][kLanes][kBlkPitch];   // [buffer][x, mean, scale]
-    stage_exp_table(s_tab);
+    const ExpTab tab = stage_exp_table(s_tab);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -192,60 +197,71 @@ rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ m
     const int64_t stream = first + lane;
     const bool live = stream < n_streams;
     const int64_t beg = live ? offsets[stream] : 0;
-    const int64_t len = live ? offsets[stream + 1] - beg : 0;
+    int64_t len = live ? offsets[stream + 1] - beg : 0;
+    const bool too_long = len > 0x7fffffffll;     // 32-bit counters: one stream of 2^31 symbols is not supported
+    if (too_long) len = 0;
     const int64_t end = beg + len;
-    // this lane's blocks, first to last: t_lo, t_lo + 1, ..., t_hi
     const int64_t t_lo = (beg + shift) >> kBlkShift, t_hi = (end - 1 + shift) >> kBlkShift;
-    const int64_t my_blocks = len > 0 ? t_hi - t_lo + 1 : 0;
-    const int64_t n_iter = warp_max_i64(my_blocks);
+    const int nb = len > 0 ? (int)(t_hi - t_lo + 1) : 0;
+    int n_iter = nb;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_iter = max(n_iter, __shfl_xor_sync(0xffffffffu, n_iter, d));
+    // symbols [j_head, kBlk) of block 0 and [0, j_tail) of block nb - 1 belong to the stream
+    const int j_ends = (int)((beg + shift) & (kBlk - 1)) | (((int)((end - 1 + shift) & (kBlk - 1)) + 1) << 4);
 
     uint64_t state = (live && init_states) ? init_states[stream] : kRansL;
-    int64_t wpos = beg;  // the stream's scratch region starts at its first symbol index
-    int32_t flags = 0;
+    uint32_t* wp = scratch + beg;  // the stream's scratch region starts at its first symbol index
+    int32_t flags = too_long ? ST_TOO_LONG : 0;
+    ParamGuard guard = guard_init();
     constexpr int kArr = kLanes * kBlkPitch, kBuf = 3 * kArr;
     float* const row = s_in[warp][0][0][lane];
     const int swz = kBlk == 8 ? ((lane >> 2) & 1) * 4 : 0;   // column j of this lane lives at j ^ swz
+    int64_t i_stage = (t_lo << kBlkShift) - shift;           // first slot of the block staged next
 
-    auto prefetch = [&](int64_t q) {
-        if (q < my_blocks) {
-            const int64_t i0 = ((t_lo + q) << kBlkShift) - shift;
-            float* d = row + (int)(q & 1) * kBuf;
-            if (i0 >= beg && i0 + kBlk <= end) {
-                cp_async_16(d + swz, x + i0);
-                cp_async_16(d + kArr + swz, mean + i0);
-                cp_async_16(d + 2 * kArr + swz, scale + i0);
+    auto stage = [&](int q) {
+        if (q < nb) {
+            float* d = row + (q & 1) * kBuf;
+            const float *px = x + i_stage, *pm = mean + i_stage, *ps = scale + i_stage;
+            const int jl = q == 0 ? (j_ends & 15) : 0, jh = q == nb - 1 ? (j_ends >> 4) : kBlk;
+            if (jl == 0 && jh == kBlk) {
+                cp_async_16(d + swz, px);
+                cp_async_16(d + kArr + swz, pm);
+                cp_async_16(d + 2 * kArr + swz, ps);
                 if (kBlk == 8) {
-                    cp_async_16(d + (4 ^ swz), x + i0 + 4);
-                    cp_async_16(d + kArr + (4 ^ swz), mean + i0 + 4);
-                    cp_async_16(d + 2 * kArr + (4 ^ swz), scale + i0 + 4);
+                    cp_async_16(d + (4 ^ swz), px + 4);
+                    cp_async_16(d + kArr + (4 ^ swz), pm + 4);
+                    cp_async_16(d + 2 * kArr + (4 ^ swz), ps + 4);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < kBlk; ++j)
-                    if (i0 + j >= beg && i0 + j < end) {
-                        cp_async_4(d + (j ^ swz), x + i0 + j);
-                        cp_async_4(d + kArr + (j ^ swz), mean + i0 + j);
-                        cp_async_4(d + 2 * kArr + (j ^ swz), scale + i0 + j);
+                    if (j >= jl && j < jh) {
+                        cp_async_4(d + (j ^ swz), px + j);
+                        cp_async_4(d + kArr + (j ^ swz), pm + j);
+                        cp_async_4(d + 2 * kArr + (j ^ swz), ps + j);
                     }
             }
+            i_stage += kBlk;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto push = [&](const SymbolTable& e) {
+        uint32_t word;
+        if (rans_push(state, e.start, e.freq, word)) *wp++ = word;
+    };
 
-    if (n_iter > 0) prefetch(0);
-    for (int64_t q = 0; q < n_iter; ++q) {
+    if (n_iter > 0) stage(0);
+    for (int q = 0; q < n_iter; ++q) {
         if (q + 1 < n_iter) {
-            prefetch(q + 1);
+            stage(q + 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        if (q < my_blocks) {
-            const int64_t i0 = ((t_lo + q) << kBlkShift) - shift;
-            const float* b = row + (int)(q & 1) * kBuf;
-            const int j_lo = i0 >= beg ? 0 : (int)(beg - i0);
-            const int j_hi = i0 + kBlk <= end ? kBlk : (int)(end - i0);
-            if (kBlk == 8 && j_lo == 0 && j_hi == kBlk) {
+        if (q < nb) {
+            const float* b = row + (q & 1) * kBuf;
+            const int jl = q == 0 ? (j_ends & 15) : 0, jh = q == nb - 1 ? (j_ends >> 4) : kBlk;
+            if (kBlk == 8 && jl == 0 && jh == kBlk) {
                 // whole block: the row comes out of shared memory as 16-byte vectors (conflict-free
                 // by the swizzle) and its eight symbols are coded from registers, fully unrolled, so
                 // that the table evaluations of later symbols fill the latencies of earlier pushes
@@ -261,25 +277,19 @@ rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ m
                     ss[4 * h] = sv.x; ss[4 * h + 1] = sv.y; ss[4 * h + 2] = sv.z; ss[4 * h + 3] = sv.w;
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const SymbolTable e = make_table(xs[k], ms[k], ss[k], s_tab, flags);
-                    uint32_t word;
-                    if (rans_push(state, e.start, e.freq, word)) scratch[wpos++] = word;
-                }
+                for (int k = 0; k < 8; ++k) push(make_table_lean(xs[k], ms[k], ss[k], tab, guard, flags));
             } else {
-                for (int j = j_lo; j < j_hi; ++j) {
+                for (int j = jl; j < jh; ++j) {
                     const int c = j ^ swz;
-                    const SymbolTable e = make_table(b[c], b[kArr + c], b[2 * kArr + c], s_tab, flags);
-                    uint32_t word;
-                    if (rans_push(state, e.start, e.freq, word)) scratch[wpos++] = word;
+                    push(make_table_lean(b[c], b[kArr + c], b[2 * kArr + c], tab, guard, flags));
                 }
             }
         }
     }
     if (live) {
-        counts[stream] = wpos - beg;
+        counts[stream] = (int64_t)(wp - (scratch + beg));
         states[stream] = state;
-        status[stream] = flags;
+        status[stream] = flags | guard_flags(guard);
     }
 }
 
