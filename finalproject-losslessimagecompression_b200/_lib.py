@@ -33,6 +33,7 @@ SIGNATURES = {
     "flic_last_error": (C.c_char_p, []),
     "flic_kernel_launches": (_i64, []),
     "flic_last_coder_kernel": (C.c_char_p, [C.c_int]),
+    "flic_set_decode_kernel": (C.c_int, [C.c_int]),
     "flic_cdf_tables": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_debug_expf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "flic_debug_part1": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libflic_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["cdf_tables.cu", "rans_encode.cu", "rans_decode.cu", "pack_words.cu", "couple_round.cu",
+SOURCES = ["cdf_tables.cu", "rans_encode.cu", "rans_decode.cu", "rans_decode_coop.cu", "pack_words.cu", "couple_round.cu",
            "flow_index.cu", "logistic_prob.cu", "capi.cu"]
 HEADERS = ["flic_core.cuh", "flic_device.cuh", "flic_kernels.cuh"]
 

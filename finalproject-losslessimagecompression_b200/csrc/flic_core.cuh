@@ -802,6 +802,26 @@ SymbolHit decode_symbol_search(uint32_t mod, float mean, float scale, ExpTab tab
     return h;
 }
 
+// The same with the model given (a caller that has it ahead of the chain keeps its ~100 cycles
+// of conversions and reciprocal out of the serial dependency).
+FLIC_HD int decode_symbol_model(uint32_t& hi, uint32_t& lo, float mean, float scale, const SymbolModel& m,
+                                ExpTab tab, ParamGuard& guard, int32_t& flags) {
+    const uint32_t mod = lo & kProbMask;
+    guard_note(guard, mean, scale);
+    const int g = guess_symbol(mod, mean, scale, m.lower);
+    int c_lo, c_hi;
+    cdf_pair(g, m, tab, c_lo, c_hi);
+    int s = g;
+    const bool left_ok = (g == m.lower) || (c_lo <= (int)mod);  // window's left edge is virtual
+    if (!(left_ok && c_hi > (int)mod)) {
+        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
+        s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
+        if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
+    }
+    rans_pop32(hi, lo, (uint32_t)c_lo, (uint32_t)(c_hi - c_lo));
+    return s;
+}
+
 FLIC_HD int decode_symbol_lean(uint32_t& hi, uint32_t& lo, float mean, float scale, ExpTab tab,
                                ParamGuard& guard, int32_t& flags) {
     const uint32_t mod = lo & kProbMask;

@@ -2,6 +2,8 @@
 #pragma once
 #include "flic_core.cuh"
 
+#include <atomic>
+
 namespace flic {
 
 // glibc's exp2f table; each TU keeps its own 256-byte constant copy and stages it into shared
@@ -38,12 +40,18 @@ __device__ __forceinline__ int64_t warp_max_i64(int64_t v) {
     return v;
 }
 
+// SM count of the CURRENT device, cached per device (a process may drive several GPUs from
+// several threads; the cache entries are written once each with the same value, so a relaxed
+// atomic per slot is enough).
 inline int sm_count() {
-    static int sms = 0;
+    constexpr int kMaxDevices = 64;
+    static std::atomic<int> cache[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    int sms = cache[dev].load(std::memory_order_relaxed);
     if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cache[dev].store(sms, std::memory_order_relaxed);
     }
     return sms;
 }

@@ -23,6 +23,10 @@
 #include "flic_device.cuh"
 #include "flic_kernels.cuh"
 
+#include <atomic>
+#include <cstdint>
+#include <cstdlib>
+
 namespace flic {
 
 // Symbols per stream per tile.  Tiles are double-buffered: while the lanes decode tile q the
@@ -328,12 +332,37 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     }
 }
 
+// Stream count up to which the CTA-per-stream kernel (rans_decode_coop.cu) is used: two CTAs of
+// it fit an SM, and within that one wave every stream decodes 1.3x (rans/test.py's mixture of
+// distributions) to 3x (narrow distributions) faster than a lane of the lane-per-stream kernel;
+// a second wave would cost more than it gains (measured crossover: 296 -> 444 streams).
+// FLIC_DEC_COOP_MAX_STREAMS overrides the count (0 disables); flic_set_decode_kernel() forces
+// either kernel.
+static std::atomic<int> g_decode_kernel{-1};
+int set_decode_kernel(int which) { return g_decode_kernel.exchange(which); }
+
+static int64_t coop_decode_max_streams() {
+    const int forced = g_decode_kernel.load(std::memory_order_relaxed);
+    if (forced == 0) return 0;
+    if (forced == 1) return INT64_MAX;
+    static const int64_t env = [] {
+        const char* e = getenv("FLIC_DEC_COOP_MAX_STREAMS");
+        return e ? (int64_t)atoll(e) : (int64_t)-1;
+    }();
+    return env >= 0 ? env : 2 * (int64_t)sm_count();
+}
+
 cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offsets,
                                const uint64_t* states, const float* mean, const float* scale,
                                const int64_t* offsets, int64_t n_streams, float* x_out,
                                uint64_t* end_states, int32_t* status, int check_end,
                                cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
+    if (n_streams <= coop_decode_max_streams()) {
+        note_coder_kernel(1, "rans_decode_coop_kernel");
+        return launch_rans_decode_coop(packed, word_offsets, states, mean, scale, offsets, n_streams, x_out,
+                                       end_states, status, check_end, stream);
+    }
     const int64_t warps = (n_streams + kLanes - 1) / kLanes;
     const bool small = warps <= (int64_t)sm_count() * 16;
     const int64_t blocks = (warps + kCoderWarps - 1) / kCoderWarps;

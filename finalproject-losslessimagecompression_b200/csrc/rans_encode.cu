@@ -24,11 +24,15 @@
 #include "flic_device.cuh"
 #include "flic_kernels.cuh"
 
+#include <atomic>
+
 namespace flic {
 
-static const char* g_last_kernel[2] = {"", ""};
-const char* last_coder_kernel(int which) { return g_last_kernel[which & 1]; }
-void note_coder_kernel(int which, const char* name) { g_last_kernel[which & 1] = name; }
+// Names are string literals; the pointers are atomics so that threads driving different GPUs
+// never read a torn value (the last writer wins, which is all a profiling aid promises).
+static std::atomic<const char*> g_last_kernel[2] = {{""}, {""}};
+const char* last_coder_kernel(int which) { return g_last_kernel[which & 1].load(std::memory_order_relaxed); }
+void note_coder_kernel(int which, const char* name) { g_last_kernel[which & 1].store(name, std::memory_order_relaxed); }
 
 // Rows a producer warp loads (and then evaluates) back to back.
 constexpr int kRowBatch = 4;

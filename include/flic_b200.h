@@ -59,6 +59,11 @@ int64_t flic_kernel_launches(void);
 /* Name of the kernel the most recent flic_rans_encode (which = 0) / flic_rans_decode (which = 1)
  * launched: the coder has a lane-per-stream and a warp-cooperative variant of each (profiling aid). */
 const char* flic_last_coder_kernel(int which);
+/* Which decode kernel flic_rans_decode launches: -1 = by stream count (default: the CTA-per-stream
+ * kernel up to two streams per SM, the lane-per-stream kernel above), 0 = always lane-per-stream,
+ * 1 = always CTA-per-stream.  Process-wide; for measurements and for tests that compare the two
+ * (their results are bit-identical by construction).  Returns the previous setting. */
+int flic_set_decode_kernel(int which);
 
 /* ------------------------------------------------------------------------------------------
  * Device entry points

@@ -300,3 +300,92 @@ def test_reciprocal_divisions_are_exact_on_the_device():
     _lib.check(L.flic_debug_div_check(n, C.c_uint64(2), 1, bad[1:2].data_ptr(), None))
     _lib.check(L.flic_debug_push_check(n, C.c_uint64(3), bad[2:3].data_ptr(), None))
     assert bad.tolist() == [0, 0, 0]
+
+
+# ---- the CTA-per-stream decoder (few streams) ----------------------------------------------------
+
+def _with_decode_kernel(which):
+    """Context manager: force the lane-per-stream (0) or the CTA-per-stream (1) decode kernel."""
+    import contextlib
+    from flic_b200 import _lib
+
+    @contextlib.contextmanager
+    def cm():
+        old = _lib.lib().flic_set_decode_kernel(which)
+        try:
+            yield
+        finally:
+            _lib.lib().flic_set_decode_kernel(old)
+    return cm()
+
+
+def _narrow(n, seed):
+    """Scales from 0.007 to 20 bins: every class of the CTA-per-stream decoder's windows (one chunk,
+    two to four chunks, none) in one stream, symbols up to five scales from the mode."""
+    rng = np.random.default_rng(seed)
+    mean = rng.normal(0, 0.7, n).astype(np.float32)
+    scale = (np.exp(rng.uniform(-5, 3, n)) / 256).astype(np.float32)
+    x = np.round((mean.astype(np.float64) + scale.astype(np.float64) * (10 * rng.random(n) - 5)) * 256) / 256
+    return x.astype(np.float32), mean, scale
+
+
+@pytest.mark.parametrize("kind", KINDS + ["narrow"])
+@pytest.mark.parametrize("n_streams", [1, 3, 48, 300])
+def test_cta_per_stream_decoder_is_bit_exact(oracle, kind, n_streams):
+    """Reference-native partitions (rans/test.py: 1 stream; trainer.py:308: 3 streams; configs[0]: 48)
+    and a full wave of CTAs: the CTA-per-stream decoder must return the symbols, end every stream at
+    1<<32, and leave exactly what the lane-per-stream kernel leaves (which the oracle pins)."""
+    from flic_b200 import rans, _lib
+    n = 60_000 if n_streams < 100 else 150_000
+    x, mean, scale = _narrow(n, 5) if kind == "narrow" else gen(kind, n, 21 + n_streams)
+    off = ragged_offsets(n, n_streams, 7 + n_streams)
+    words_o, woff_o, states_o, _ = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+    xd, md, sd = _cuda(x, mean, scale)
+    offd = torch.from_numpy(off).cuda()
+    enc = rans.encode_streams(xd, md, sd, offd)
+    assert np.array_equal(_u32(enc.words), words_o) and np.array_equal(_u64(enc.final_states), states_o)
+    with _with_decode_kernel(1):
+        xr, end, status = rans.decode_streams(enc, md, sd, offd)
+        assert _lib.lib().flic_last_coder_kernel(1).decode() == "rans_decode_coop_kernel"
+    assert not status.any().item()
+    assert torch.equal(xr, xd)
+    assert bool((end == (1 << 32)).all().item())
+    with _with_decode_kernel(0):
+        xr0, end0, status0 = rans.decode_streams(enc, md, sd, offd)
+        assert _lib.lib().flic_last_coder_kernel(1).decode() != "rans_decode_coop_kernel"
+    assert torch.equal(xr0, xr) and torch.equal(end0, end) and torch.equal(status0, status)
+
+
+def test_cta_per_stream_decoder_reports_what_the_lane_kernel_reports():
+    """Truncated buffers, zero / negative / non-finite scales and absurd means: same status bits from
+    both decode kernels, no crash, no out-of-bounds access (run under compute-sanitizer by hand)."""
+    from flic_b200 import rans, _lib
+    x, mean, scale = gen("test", 20_000, 3)
+    xd, md, sd = _cuda(x, mean, scale)
+    off = torch.tensor([0, 5000, 5000, 12_345, 20_000], device="cuda")
+    enc = rans.encode_streams(xd, md, sd, off)
+    woff = enc.word_offsets.clone()
+    # stream 0: three words short; stream 2: parameters damaged
+    bad_m, bad_s = md.clone(), sd.clone()
+    bad_s[6000] = 0.0
+    bad_s[7000] = -1.0
+    bad_s[8000] = float("nan")
+    bad_m[9000] = 1.0e9
+    words = enc.words.clone()
+    cut = rans.EncodedStreams(words, woff, enc.final_states, enc.status, enc.n_symbols)
+    cut.word_offsets = woff.clone()
+    res = []
+    for which in (0, 1):
+        with _with_decode_kernel(which):
+            # shorten stream 0 by pretending its words end three early (the words stay in place)
+            wo = woff.clone()
+            e = rans.EncodedStreams(torch.cat([words[:int(woff[1]) - 3], words[int(woff[1]):]]),
+                                    torch.cat([wo[:1], wo[1:] - 3]), enc.final_states, enc.status, enc.n_symbols)
+            xr, end, status = rans.decode_streams(e, bad_m, bad_s, off)
+            res.append(status.cpu().tolist())
+    assert res[0] == res[1]
+    st = res[1]
+    assert st[0] & (_lib.ST_UNDERRUN | _lib.ST_BAD_END_STATE | _lib.ST_NO_SYMBOL)
+    assert st[1] == 0                      # the empty stream
+    assert st[2] & _lib.ST_ZERO_SCALE and st[2] & _lib.ST_NONFINITE
+    assert st[3] == 0
