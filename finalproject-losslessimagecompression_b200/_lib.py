@@ -44,6 +44,8 @@ SIGNATURES = {
     "flic_encode_workspace_bytes": (_i64, [_i64, _i64]),
     "flic_rans_encode": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_rans_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp]),
+    "flic_rans_decode_resume": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "flic_gather_words": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "flic_couple_add_round": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp]),
     "flic_u8_to_grid": (C.c_int, [_vp, _vp, _i64, _vp]),
     "flic_grid_to_u8": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -81,7 +83,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the header and the library drifted apart
             fn.restype = res
             fn.argtypes = args
-        if L.flic_abi_version() != 1:
+        if L.flic_abi_version() != 2:
             raise FlicError("libflic_b200.so ABI version mismatch")
         _lib = L
     return _lib

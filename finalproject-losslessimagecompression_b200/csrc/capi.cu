@@ -142,17 +142,39 @@ int flic_rans_encode(const float* x, const float* mean, const float* scale,
     return 0;
 }
 
+int flic_rans_decode_resume(const uint32_t* packed, const int64_t* word_offsets,
+                            const uint64_t* states_in, const int64_t* words_left_in, const float* mean,
+                            const float* scale, const int64_t* stream_offsets, int64_t n_streams,
+                            float* x_out, uint64_t* end_states, int64_t* words_left_out, int32_t* status,
+                            int check_end, flic_cuda_stream_t stream) {
+    if (n_streams < 0) return fail(FLIC_E_ARG, "n_streams < 0");
+    if (n_streams == 0) return 0;
+    if (!word_offsets || !states_in || !stream_offsets || !end_states || !status)
+        return fail(FLIC_E_ARG, "null pointer");
+    const flic::WordsLeft left = {words_left_in, words_left_out};
+    FLIC_CUDA(flic::launch_rans_decode(packed, word_offsets, states_in, mean, scale, stream_offsets,
+                                       n_streams, x_out, end_states, status, check_end, left, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
 int flic_rans_decode(const uint32_t* packed, const int64_t* word_offsets,
                      const uint64_t* final_states, const float* mean, const float* scale,
                      const int64_t* stream_offsets, int64_t n_streams, float* x_out,
                      uint64_t* end_states, int32_t* status, int check_end,
                      flic_cuda_stream_t stream) {
-    if (n_streams < 0) return fail(FLIC_E_ARG, "n_streams < 0");
+    return flic_rans_decode_resume(packed, word_offsets, final_states, nullptr, mean, scale, stream_offsets,
+                                   n_streams, x_out, end_states, nullptr, status, check_end, stream);
+}
+
+int flic_gather_words(const uint32_t* src, const int64_t* src_offsets, const int64_t* dst_starts,
+                      int64_t n_streams, uint32_t* dst, int64_t dst_capacity, int32_t* status,
+                      flic_cuda_stream_t stream) {
+    if (n_streams < 0 || dst_capacity < 0) return fail(FLIC_E_ARG, "negative size");
     if (n_streams == 0) return 0;
-    if (!word_offsets || !final_states || !stream_offsets || !end_states || !status)
-        return fail(FLIC_E_ARG, "null pointer");
-    FLIC_CUDA(flic::launch_rans_decode(packed, word_offsets, final_states, mean, scale, stream_offsets,
-                                       n_streams, x_out, end_states, status, check_end, (cudaStream_t)stream));
+    if (!src_offsets || !dst_starts || (dst_capacity > 0 && (!src || !dst))) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(flic::launch_gather_words(src, src_offsets, dst_starts, n_streams, dst, dst_capacity, status,
+                                        (cudaStream_t)stream));
     g_launches += 1;
     return 0;
 }
@@ -542,7 +564,7 @@ int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_
         FLIC_CUDA(cudaEventRecord(c->done[slot], st));
         sl.busy = true;
         FLIC_CUDA(flic::launch_rans_decode(sl.packed, sl.word_offsets, sl.states, sl.mean, sl.scale,
-                                           sl.offsets, ns, sl.x, sl.end_states, sl.status, 1, st));
+                                           sl.offsets, ns, sl.x, sl.end_states, sl.status, 1, flic::WordsLeft{nullptr, nullptr}, st));
         g_launches += 1;
         if (n > 0) FLIC_CUDA(cudaMemcpyAsync(x_out + a, sl.x, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
         if (end_states_out)

@@ -35,6 +35,12 @@ cudaError_t launch_rans_encode(const float* x, const float* mean, const float* s
                                const uint64_t* init_states, uint32_t* scratch, int64_t* counts,
                                uint64_t* states, int32_t* status, cudaStream_t stream);
 
+// Copy every stream's words to a destination of its own: dst[dst_starts[s] + i] = src[src_offsets[s] + i]
+// for i < src_offsets[s + 1] - src_offsets[s] (concatenating the levels of a chained stream).
+cudaError_t launch_gather_words(const uint32_t* src, const int64_t* src_offsets, const int64_t* dst_starts,
+                                int64_t n_streams, uint32_t* dst, int64_t dst_capacity, int32_t* status,
+                                cudaStream_t stream);
+
 // K4: exclusive scan of counts -> word_offsets[n_streams + 1]; gather scratch -> packed.
 // scan_tmp needs scan_tmp_elems(n_streams) int64 elements.
 int64_t scan_tmp_elems(int64_t n_streams);
@@ -44,12 +50,20 @@ cudaError_t launch_pack_words(const uint32_t* scratch, const int64_t* offsets,
                               const int64_t* word_offsets, int64_t n_streams, uint32_t* packed,
                               int64_t packed_capacity, int32_t* status, cudaStream_t stream);
 
+// Continuation of a decode across calls (coder.py:29-38 chains one state through the levels):
+// stream s has in[s] unread words at packed[word_offsets[s] ...] when the call starts (null: all
+// of word_offsets[s + 1] - word_offsets[s]) and out[s] when it returns (null: not reported).
+struct WordsLeft {
+    const int64_t* in;
+    int64_t* out;
+};
+
 // K3: per-stream rANS decode (search + state update), symbols written in forward order.
 cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offsets,
                                const uint64_t* states, const float* mean, const float* scale,
                                const int64_t* offsets, int64_t n_streams, float* x_out,
                                uint64_t* end_states, int32_t* status, int check_end,
-                               cudaStream_t stream);
+                               WordsLeft left, cudaStream_t stream);
 
 // K3c: the same for few streams -- one CTA per stream, exact CDF windows tabulated ahead of the
 // serial chain by producer warps (rans_decode_coop.cu).  launch_rans_decode picks it by stream count.
@@ -57,7 +71,7 @@ cudaError_t launch_rans_decode_coop(const uint32_t* packed, const int64_t* word_
                                     const uint64_t* states, const float* mean, const float* scale,
                                     const int64_t* offsets, int64_t n_streams, float* x_out,
                                     uint64_t* end_states, int32_t* status, int check_end,
-                                    cudaStream_t stream);
+                                    WordsLeft left, cudaStream_t stream);
 
 // K5: x[:, a_ch:, :, :] += sign * Round_nbits(t)            couplelib.py:49-51,58-59; roundlib.py:18-38
 //   x: (batch, channels, hw) contiguous;  t: (batch, channels - a_ch, hw) contiguous

@@ -130,4 +130,34 @@ cudaError_t launch_pack_words(const uint32_t* scratch, const int64_t* offsets,
     return cudaGetLastError();
 }
 
+// One warp per stream, like pack_words_kernel, with the destination given per stream.
+__global__ void __launch_bounds__(256)
+gather_words_kernel(const uint32_t* __restrict__ src, const int64_t* __restrict__ src_offsets,
+                    const int64_t* __restrict__ dst_starts, int64_t n_streams, uint32_t* __restrict__ dst,
+                    int64_t capacity, int32_t* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_streams; s += warps_total) {
+        const int64_t a = src_offsets[s], cnt = src_offsets[s + 1] - a, d = dst_starts[s];
+        if (d < 0 || d + cnt > capacity) {
+            if (lane == 0 && status) atomicOr(status + s, ST_UNDERRUN);
+            continue;
+        }
+        for (int64_t k = lane; k < cnt; k += 32) dst[d + k] = src[a + k];
+    }
+}
+
+cudaError_t launch_gather_words(const uint32_t* src, const int64_t* src_offsets, const int64_t* dst_starts,
+                                int64_t n_streams, uint32_t* dst, int64_t dst_capacity, int32_t* status,
+                                cudaStream_t stream) {
+    if (n_streams <= 0) return cudaSuccess;
+    const int warps_per_cta = 8;
+    int64_t blocks = (n_streams + warps_per_cta - 1) / warps_per_cta;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    gather_words_kernel<<<(unsigned)blocks, warps_per_cta * 32, 0, stream>>>(src, src_offsets, dst_starts, n_streams,
+                                                                           dst, dst_capacity, status);
+    return cudaGetLastError();
+}
+
 }  // namespace flic

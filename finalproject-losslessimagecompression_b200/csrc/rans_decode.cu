@@ -53,7 +53,7 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
                    const uint64_t* __restrict__ states, const float* __restrict__ mean,
                    const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                    int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
-                   int32_t* __restrict__ status, int check_end) {
+                   int32_t* __restrict__ status, int check_end, WordsLeft left) {
     __shared__ __align__(256) uint64_t s_tab[32];
     __shared__ float2 s_tile[WARPS][2][kLanes][kDecTile + 1];
     const ExpTab tab = stage_exp_table(s_tab);
@@ -68,7 +68,8 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
     const int64_t beg = live ? offsets[stream] : 0;
     int64_t len = live ? offsets[stream + 1] - beg : 0;
     const int64_t wbeg = live ? word_offsets[stream] : 0;
-    const int64_t wcount = live ? word_offsets[stream + 1] - wbeg : 0;
+    int64_t wcount = live ? word_offsets[stream + 1] - wbeg : 0;
+    if (live && left.in) wcount = left.in[stream] < 0 ? 0 : (left.in[stream] < wcount ? left.in[stream] : wcount);
     const bool too_long = wcount > 0xffffffffll;
     if (too_long) len = 0;
     const int64_t max_len = warp_max_i64(len);
@@ -147,6 +148,7 @@ rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
         if (check_end && !too_long && (state != kRansL || wrem != 0)) flags |= ST_BAD_END_STATE;
         end_states[stream] = state;
         status[stream] = flags;
+        if (left.out) left.out[stream] = (int64_t)wrem;
     }
 }
 
@@ -188,7 +190,7 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                         const uint64_t* __restrict__ states, const float* __restrict__ mean,
                         const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                         int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
-                        int32_t* __restrict__ status, int check_end, int shift) {
+                        int32_t* __restrict__ status, int check_end, WordsLeft left, int shift) {
     __shared__ __align__(256) uint64_t s_tab[32];
     // [buffer][mean, scale][lane][kBlkPitch]
     __shared__ __align__(16) float s_par[WARPS][2][2][kLanes][kBlkPitch];
@@ -204,7 +206,8 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     const int64_t beg = live ? offsets[stream] : 0;
     int64_t len = live ? offsets[stream + 1] - beg : 0;
     const int64_t wbeg = live ? word_offsets[stream] : 0;
-    const int64_t wcount = live ? word_offsets[stream + 1] - wbeg : 0;
+    int64_t wcount = live ? word_offsets[stream + 1] - wbeg : 0;
+    if (live && left.in) wcount = left.in[stream] < 0 ? 0 : (left.in[stream] < wcount ? left.in[stream] : wcount);
     // 32-bit counters: a single stream of 2^31 symbols (or words) is not supported
     const bool too_long = wcount > 0x7fffffffll || len > 0x7fffffffll;
     if (too_long) len = 0;
@@ -329,6 +332,7 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         if (check_end && !too_long && (state != kRansL || wrem != 0)) flags |= ST_BAD_END_STATE;
         end_states[stream] = state;
         status[stream] = flags;
+        if (left.out) left.out[stream] = wrem > 0 ? (int64_t)wrem : 0;
     }
 }
 
@@ -356,12 +360,12 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
                                const uint64_t* states, const float* mean, const float* scale,
                                const int64_t* offsets, int64_t n_streams, float* x_out,
                                uint64_t* end_states, int32_t* status, int check_end,
-                               cudaStream_t stream) {
+                               WordsLeft left, cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
     if (n_streams <= coop_decode_max_streams()) {
         note_coder_kernel(1, "rans_decode_coop_kernel");
         return launch_rans_decode_coop(packed, word_offsets, states, mean, scale, offsets, n_streams, x_out,
-                                       end_states, status, check_end, stream);
+                                       end_states, status, check_end, left, stream);
     }
     const int64_t warps = (n_streams + kLanes - 1) / kLanes;
     const bool small = warps <= (int64_t)sm_count() * 16;
@@ -375,16 +379,16 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
     if (lane_staged) {
         if (small)
             rans_decode_lane_kernel<1><<<(unsigned)warps, 32, 0, stream>>>(
-                packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, sh_m);
+                packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, left, sh_m);
         else
             rans_decode_lane_kernel<kCoderWarps><<<(unsigned)blocks, kCoderWarps * 32, 0, stream>>>(
-                packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, sh_m);
+                packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, left, sh_m);
     } else if (small) {
         rans_decode_kernel<1><<<(unsigned)warps, 32, 0, stream>>>(
-            packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end);
+            packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, left);
     } else {
         rans_decode_kernel<kCoderWarps><<<(unsigned)blocks, kCoderWarps * 32, 0, stream>>>(
-            packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end);
+            packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, left);
     }
     return cudaGetLastError();
 }

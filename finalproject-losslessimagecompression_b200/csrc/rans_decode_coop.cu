@@ -116,7 +116,7 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                         const uint64_t* __restrict__ states, const float* __restrict__ mean,
                         const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                         int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
-                        int32_t* __restrict__ status, int check_end) {
+                        int32_t* __restrict__ status, int check_end, WordsLeft left) {
     extern __shared__ __align__(256) unsigned char s_raw[];
     uint64_t* const s_tab = reinterpret_cast<uint64_t*>(s_raw);                              // 256 B
     int* const s_code = reinterpret_cast<int*>(s_raw + 512);                                 // 32 x 4 B (consumer only)
@@ -133,7 +133,8 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     const int64_t beg = offsets[stream];
     int64_t len = offsets[stream + 1] - beg;
     const int64_t wbeg = word_offsets[stream];
-    const int64_t wcount = word_offsets[stream + 1] - wbeg;
+    int64_t wcount = word_offsets[stream + 1] - wbeg;
+    if (left.in) wcount = left.in[stream] < 0 ? 0 : (left.in[stream] < wcount ? left.in[stream] : wcount);
     const bool too_long = wcount > 0x7fffffffll || len > 0x7fffffffll;
     if (too_long) len = 0;
     const int n_groups = (int)((len + 31) >> 5);
@@ -460,6 +461,7 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
             if (check_end && !too_long && (state != kRansL || wrem != 0)) flags |= ST_BAD_END_STATE;
             end_states[stream] = state;
             status[stream] = flags;
+            if (left.out) left.out[stream] = wrem > 0 ? (int64_t)wrem : 0;
         }
     }
 }
@@ -470,13 +472,13 @@ cudaError_t launch_rans_decode_coop(const uint32_t* packed, const int64_t* word_
                                     const uint64_t* states, const float* mean, const float* scale,
                                     const int64_t* offsets, int64_t n_streams, float* x_out,
                                     uint64_t* end_states, int32_t* status, int check_end,
-                                    cudaStream_t stream) {
+                                    WordsLeft left, cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(rans_decode_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kCoopSmemBytes);
     if (e != cudaSuccess) return e;
     rans_decode_coop_kernel<<<(unsigned)n_streams, (kCoopProducers + 1) * 32, kCoopSmemBytes, stream>>>(
-        packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end);
+        packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, left);
     return cudaGetLastError();
 }
 

@@ -230,9 +230,12 @@ class IDFlows(nn.Module):
         off = (base[:, None] + cuts[None, :]).reshape(-1)
         return torch.cat([off, torch.tensor([n_img * seg], dtype=torch.int64, device=device)])
 
-    def _chunk_forward(self, x, cond, n_real, sps, stats):
-        """x: (codec_batch, C, H, W) grid floats -> list of EncodedStreams, one per level."""
+    def _chunk_forward(self, x, cond, n_real, sps, stats, chain, slot):
+        """x: (codec_batch, C, H, W) grid floats -> list of EncodedStreams: one per level, or a single
+        one holding each image's levels chained (coder.py:18-27).  Nothing here waits for the GPU:
+        the word arrays keep their worst-case capacity until CompressedBatch.finalize() trims them."""
         out = []
+        carried = None
         for level in range(self.nsplit):
             block = self.blocks[level]
             x, _ = block["extend"](x, None)
@@ -251,8 +254,15 @@ class IDFlows(nn.Module):
                 stats.append((z, mean, logscale))
             off = self._segment_offsets(level, n_real, sps, x.device)
             n = int(n_real * math.prod(self.latents_shape[level]))
-            out.append(rans.encode_streams(z.reshape(-1)[:n], mean.reshape(-1)[:n], scale.reshape(-1)[:n], off))
-        return out
+            ws = self.__dict__.setdefault("_enc_ws", {}).setdefault((x.device.index, slot, level), rans.Workspace())
+            enc = rans.encode_streams(z.reshape(-1)[:n], mean.reshape(-1)[:n], scale.reshape(-1)[:n], off,
+                                      init_states=carried, workspace=ws, own_output=False, validate=False)
+            if chain:
+                carried = enc.final_states          # the next level continues every image's stream
+            else:
+                enc.words = enc.words[:max(n, 1)].clone()   # the workspace is reused by the next chunk of this slot
+            out.append(enc)
+        return [rans.chain_levels(out)] if chain else out
 
     def _pipes(self, dev, n_chunks: int, pipeline: int):
         """Side CUDA streams for chunk-level pipelining, or [None] for in-line.
@@ -269,7 +279,7 @@ class IDFlows(nn.Module):
 
     def compress(self, images: torch.Tensor, cond: torch.Tensor | None = None, codec_batch: int | None = None,
                  streams_per_segment: int = 1, check: bool = True, stats: list | None = None,
-                 pipeline: int = 2) -> CompressedBatch:
+                 pipeline: int = 2, chain_levels: bool | None = None) -> CompressedBatch:
         """Lossless compression of uint8 images (N, C, H, W) on the GPU.
 
         codec_batch: images per network pass (default: all of them).  It is recorded in the
@@ -277,32 +287,40 @@ class IDFlows(nn.Module):
         bit-identical prior outputs; the last chunk is padded with zero images whose streams are
         not stored.  streams_per_segment: rANS streams per (image, level); 0 selects the
         reference's native partition (one stream per level per chunk, trainer.py:308-315).
+        chain_levels: carry each image's rANS state from one latent level into the next, as the
+        reference's coder.Encode does (coder.py:18-27): one stream -- one 64-bit final state --
+        per image instead of one per image and level, which is what keeps the container within
+        0.1 % of the reference's native partition (one stream per level per batch).  Default: on
+        when streams_per_segment == 1.
         pipeline: chunks in flight.  Chunks are independent, so chunk i runs on CUDA stream
         i % pipeline: the coder kernels of one chunk (a few dozen serial streams, latency-bound,
         a handful of warps) overlap the convolutions of the next one instead of idling the GPU
         between them.  The bytes produced do not depend on it."""
         if images.dtype != torch.uint8 or images.dim() != 4:
             raise TypeError("images must be uint8 (N, C, H, W)")
-        return self._compress(images, True, cond, codec_batch, streams_per_segment, check, stats, pipeline)
+        return self._compress(images, True, cond, codec_batch, streams_per_segment, check, stats, pipeline, chain_levels)
 
     def compress_grid(self, x: torch.Tensor, cond: torch.Tensor | None = None, codec_batch: int | None = None,
                       streams_per_segment: int = 1, check: bool = True, stats: list | None = None,
-                      pipeline: int = 2) -> CompressedBatch:
+                      pipeline: int = 2, chain_levels: bool | None = None) -> CompressedBatch:
         """compress() for inputs that are already on the 2^-nbits grid as float32 (N, C, H, W) --
         residuals and pooled images of the two-level model (flows.py:212-214) are such tensors and
         are not 8-bit pixel values."""
         if x.dtype != torch.float32 or x.dim() != 4:
             raise TypeError("x must be float32 (N, C, H, W) with values on the 2^-nbits grid")
-        return self._compress(x, False, cond, codec_batch, streams_per_segment, check, stats, pipeline)
+        return self._compress(x, False, cond, codec_batch, streams_per_segment, check, stats, pipeline, chain_levels)
 
-    def _compress(self, images, from_u8, cond, codec_batch, streams_per_segment, check, stats, pipeline):
+    def _compress(self, images, from_u8, cond, codec_batch, streams_per_segment, check, stats, pipeline, chain_levels=None):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise _lib.FlicError("compress needs the model on a CUDA device (no CPU fallback)")
         images = images.to(dev, non_blocking=True)
         n = images.shape[0]
         cbs = int(codec_batch or max(n, 1))
-        batch = CompressedBatch(n, (self.C, self.H, self.W), self.nsplit, cbs, int(streams_per_segment))
+        chain = (int(streams_per_segment) == 1) if chain_levels is None else bool(chain_levels)
+        if chain and int(streams_per_segment) != 1:
+            raise ValueError("chain_levels needs one stream per image (streams_per_segment == 1)")
+        batch = CompressedBatch(n, (self.C, self.H, self.W), self.nsplit, cbs, int(streams_per_segment), chained=chain)
         if cond is not None:
             cond = cond.to(dev)
         with deterministic_convs(), torch.cuda.device(dev):
@@ -321,14 +339,19 @@ class IDFlows(nn.Module):
                         x = torch.cat([x, x.new_zeros((cbs - n_real,) + tuple(x.shape[1:]))])
                         if c is not None:
                             c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
-                    section = self._chunk_forward(x, c, n_real, int(streams_per_segment), stats)
+                    section = self._chunk_forward(x, c, n_real, int(streams_per_segment), stats, chain, ci % len(pipes))
                     if side is not None:
                         for e in section:
                             e.record_stream(main)
                     batch.sections.append(section)
+                # word arrays keep their worst-case size until trimmed, which needs the word counts on
+                # the host: trim the chunk two rounds back, whose kernels have long finished
+                if ci >= 2 * len(pipes):
+                    batch.finalize(ci - 2 * len(pipes))
             for side in pipes:
                 if side is not None:
                     main.wait_stream(side)
+        batch.finalize()
         if check:
             for ch in batch.sections:
                 for e in ch:
@@ -374,6 +397,7 @@ class IDFlows(nn.Module):
                         c = torch.cat([c, c.new_zeros((cbs - n_real,) + tuple(c.shape[1:]))])
                     conds = self._cond_pyramid(c)
                     x = None
+                    carried = left = None
                     for level in reversed(range(self.nsplit)):
                         block = self.blocks[level]
                         cz, h, w = self.latents_shape[level]
@@ -386,8 +410,17 @@ class IDFlows(nn.Module):
                         nsym = n_real * cz * h * w
                         off = self._segment_offsets(level, n_real, sps, dev)
                         z = torch.zeros((cbs, cz, h, w), dtype=torch.float32, device=dev)
-                        _, _, st = rans.decode_streams(batch.sections[ci][level], mean.reshape(-1)[:nsym],
-                                                       scale.reshape(-1)[:nsym], off, out=z.view(-1)[:nsym])
+                        if batch.chained:
+                            # every image's one stream, continued: this level starts from the state and
+                            # the unread words the later level's decode stopped at (coder.py:29-38)
+                            _, carried, st, left = rans.decode_streams(
+                                batch.sections[ci][0], mean.reshape(-1)[:nsym], scale.reshape(-1)[:nsym], off,
+                                out=z.view(-1)[:nsym], check_end=level == 0, validate=False,
+                                states=carried, words_left=left, return_words_left=True)
+                        else:
+                            _, _, st = rans.decode_streams(batch.sections[ci][level], mean.reshape(-1)[:nsym],
+                                                           scale.reshape(-1)[:nsym], off, out=z.view(-1)[:nsym],
+                                                           validate=False)
                         statuses.append(st)
                         x = z if level == self.nsplit - 1 else torch.cat((z, x), dim=1)
                         x = self._flow_backward(block, x)
@@ -399,7 +432,7 @@ class IDFlows(nn.Module):
                         img = x[:n_real].contiguous()
                     outs.append(img)
                     if side is not None:
-                        for t in statuses[-(self.nsplit + 1):]:
+                        for t in statuses[-(self.nsplit + (1 if to_u8 else 0)):]:
                             t.record_stream(main)
                         img.record_stream(main)
             for side in pipes:

@@ -50,13 +50,24 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous().view(-1)
 
 
-def _offsets(stream_offsets, n_symbols: int, device: torch.device) -> torch.Tensor:
-    """int64[n_streams+1] on `device`; None means one stream over everything."""
+def _offsets(stream_offsets, n_symbols: int, device: torch.device, validate: bool = True) -> torch.Tensor:
+    """int64[n_streams+1] on `device`; None means one stream over everything.
+
+    The kernels index the symbol arrays with these numbers, so a partition that does not start at
+    0, runs backwards or ends beyond the arrays reads and writes out of bounds.  Offsets that
+    arrive on the host are checked for free; CUDA tensors cost one synchronising reduction, which
+    `validate=False` skips for callers that build the partition themselves (the flow does)."""
     if stream_offsets is None:
         return torch.tensor([0, n_symbols], dtype=torch.int64, device=device)
     off = torch.as_tensor(stream_offsets, dtype=torch.int64)
     if off.dim() != 1 or off.numel() < 1:
         raise ValueError("stream_offsets must be 1-D with at least one entry")
+    if validate:
+        bad = (off[0] != 0) | (off[-1] > n_symbols)
+        if off.numel() > 1:
+            bad = bad | (off[1:] < off[:-1]).any()
+        if bool(bad):
+            raise ValueError("stream_offsets must start at 0, be non-decreasing and end within the symbol arrays")
     return off.to(device).contiguous()
 
 
@@ -151,7 +162,7 @@ _default_ws: dict = {}
 
 
 def encode_streams(x, mean, scale, stream_offsets=None, init_states=None, workspace: Workspace | None = None,
-                   own_output: bool = True) -> EncodedStreams:
+                   own_output: bool = True, validate: bool = True) -> EncodedStreams:
     """rANS-encode every stream [stream_offsets[s], stream_offsets[s+1]) of the flat symbol arrays.
 
     x, mean, scale: float32 CUDA tensors of equal numel (any shape; flattened row-major, which is
@@ -164,7 +175,7 @@ def encode_streams(x, mean, scale, stream_offsets=None, init_states=None, worksp
     if mv.numel() != n or sv.numel() != n:
         raise ValueError("x, mean, scale must have the same number of elements")
     dev = xv.device
-    off = _offsets(stream_offsets, n, dev)
+    off = _offsets(stream_offsets, n, dev, validate)
     ns = off.numel() - 1
     ws = workspace or _default_ws.setdefault((dev.index, _stream_ptr(dev)), Workspace())
     buf, packed = ws.get(n, ns, dev)
@@ -188,15 +199,22 @@ def encode_streams(x, mean, scale, stream_offsets=None, init_states=None, worksp
 
 
 def decode_streams(enc: EncodedStreams, mean, scale, stream_offsets=None, check_end: bool = True,
-                   out: torch.Tensor | None = None):
+                   out: torch.Tensor | None = None, validate: bool = True, states: torch.Tensor | None = None,
+                   words_left: torch.Tensor | None = None, return_words_left: bool = False):
     """Inverse of encode_streams.  Returns (x float32[n_symbols], end_states int64[n_streams],
-    status int32[n_streams]); x is in forward order.  Asynchronous on the current stream."""
+    status int32[n_streams]); x is in forward order.  Asynchronous on the current stream.
+
+    Continuation (coder.py:29-38 chains one state through the levels): `states` replaces
+    enc.final_states as the states to start from, `words_left` (int64 per stream) says how many
+    of each stream's words are still unread, and with return_words_left the unread counts after
+    this call are returned as a fourth value.  A chained stream is decoded level by level, last
+    level first, feeding each call's (end_states, words_left) into the next."""
     mv, sv = _f32c(mean, "mean"), _f32c(scale, "scale")
     n = mv.numel()
     if sv.numel() != n:
         raise ValueError("mean and scale must have the same number of elements")
     dev = mv.device
-    off = _offsets(stream_offsets, n, dev)
+    off = _offsets(stream_offsets, n, dev, validate)
     ns = off.numel() - 1
     if enc.final_states.numel() != ns or enc.word_offsets.numel() != ns + 1:
         raise ValueError("encoded stream count does not match stream_offsets")
@@ -206,12 +224,63 @@ def decode_streams(enc: EncodedStreams, mean, scale, stream_offsets=None, check_
     end_states = torch.empty(ns, dtype=torch.int64, device=dev)
     status = torch.empty(ns, dtype=torch.int32, device=dev)
     words = enc.words.to(dev)
+    word_offsets = enc.word_offsets.to(dev)
+    if validate and ns > 0 and int(word_offsets[-1].item()) > words.numel():
+        raise ValueError("word_offsets end beyond the word array")
+    st_in = enc.final_states if states is None else states
+    st_in = st_in.to(device=dev, dtype=torch.int64).contiguous()
+    if st_in.numel() != ns:
+        raise ValueError("states must have one entry per stream")
+    left_in_ptr = 0
+    if words_left is not None:
+        words_left = words_left.to(device=dev, dtype=torch.int64).contiguous()
+        if words_left.numel() != ns:
+            raise ValueError("words_left must have one entry per stream")
+        left_in_ptr = words_left.data_ptr()
+    left_out = torch.empty(ns, dtype=torch.int64, device=dev) if return_words_left else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().flic_rans_decode(
-            words.data_ptr(), enc.word_offsets.to(dev).data_ptr(), enc.final_states.to(dev).data_ptr(),
+        _lib.check(_lib.lib().flic_rans_decode_resume(
+            words.data_ptr(), word_offsets.data_ptr(), st_in.data_ptr(), left_in_ptr,
             mv.data_ptr(), sv.data_ptr(), off.data_ptr(), ns, x_out.data_ptr(), end_states.data_ptr(),
-            status.data_ptr(), int(bool(check_end)), _stream_ptr(dev)), "flic_rans_decode")
+            left_out.data_ptr() if left_out is not None else 0, status.data_ptr(), int(bool(check_end)),
+            _stream_ptr(dev)), "flic_rans_decode_resume")
+    if return_words_left:
+        return x_out, end_states, status, left_out
     return x_out, end_states, status
+
+
+def chain_levels(levels: list) -> EncodedStreams:
+    """Concatenate, stream by stream, the words of EncodedStreams that were encoded one after the
+    other with the state carried from each into the next (init_states = previous final_states):
+    the result is what the reference's chained coder.Encode (coder.py:18-27) produces per stream --
+    the last level's state and every level's words in emission order.  Asynchronous; no host sync."""
+    if not levels:
+        raise ValueError("no levels")
+    dev = levels[0].words.device
+    ns = levels[0].n_streams
+    counts = [e.word_offsets[1:] - e.word_offsets[:-1] for e in levels]
+    total = counts[0].clone()
+    for c in counts[1:]:
+        if c.numel() != ns:
+            raise ValueError("levels must have the same streams")
+        total = total + c
+    word_offsets = torch.zeros(ns + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(total, 0, out=word_offsets[1:])
+    capacity = sum(max(e.n_symbols, 0) for e in levels)
+    if any(e.n_symbols < 0 for e in levels):       # streams that came out of a container: exact sizes are known
+        capacity = sum(int(e.word_offsets[-1].item()) for e in levels)
+    words = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
+    status = levels[0].status.clone()
+    for e in levels[1:]:
+        status |= e.status
+    start = word_offsets[:-1].clone()
+    with torch.cuda.device(dev):
+        for e, c in zip(levels, counts):
+            _lib.check(_lib.lib().flic_gather_words(e.words.data_ptr(), e.word_offsets.data_ptr(), start.data_ptr(), ns,
+                                                    words.data_ptr(), words.numel(), status.data_ptr(), _stream_ptr(dev)),
+                       "flic_gather_words")
+            start = start + c
+    return EncodedStreams(words, word_offsets, levels[-1].final_states, status, sum(max(e.n_symbols, 0) for e in levels))
 
 
 def check_status(status: torch.Tensor) -> None:

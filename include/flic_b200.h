@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FLIC_ABI_VERSION 1
+#define FLIC_ABI_VERSION 2
 
 /* negative return codes */
 #define FLIC_E_ARG (-1)      /* bad argument (null pointer, negative size, offsets not monotone) */
@@ -119,6 +119,33 @@ int flic_rans_decode(const uint32_t* packed, const int64_t* word_offsets,
                      const int64_t* stream_offsets, int64_t n_streams, float* x_out,
                      uint64_t* end_states, int32_t* status, int check_end,
                      flic_cuda_stream_t stream);
+
+/* K3 with a continuation (ABI 2).  coder.Encode / coder.Decode (coder.py:18-38) carry ONE state
+ * through the latent levels of a batch: encode level 0, 1, 2 from the state the previous level
+ * ended in, decode level 2, 1, 0 from the state the later level's decode ended in.  rANS is LIFO, so
+ * that decode order is also the dependency order of a real decompress (the prior of level k needs
+ * the decoded level k + 1).  A chained stream is encoded with flic_rans_encode's init_states and
+ * its levels' words concatenated in emission order (flic_gather_words); each level is then decoded
+ * with this call, which starts from states_in with words_left_in[s] unread words at
+ * packed[word_offsets[s] ...] (null: the stream's whole word_offsets range) and reports the state
+ * and the unread count it stops at.  The word a later level's FIRST symbol pushed is pulled when
+ * the earlier level's decode starts -- from the same array, which is what the reference's
+ * per-level buffers get wrong.  check_end belongs on the last call (level 0).
+ *   words_left_in   int64[n_streams], device, or null
+ *   words_left_out  int64[n_streams], device (out), or null */
+int flic_rans_decode_resume(const uint32_t* packed, const int64_t* word_offsets,
+                            const uint64_t* states_in, const int64_t* words_left_in, const float* mean,
+                            const float* scale, const int64_t* stream_offsets, int64_t n_streams,
+                            float* x_out, uint64_t* end_states, int64_t* words_left_out, int32_t* status,
+                            int check_end, flic_cuda_stream_t stream);
+
+/* K4 for chained streams: dst[dst_starts[s] + i] = src[src_offsets[s] + i] for every word i of
+ * stream s (src_offsets has n_streams + 1 entries).  Replaces the list appends of
+ * coder.py:26 / trainer.py:321.  A destination outside [0, dst_capacity) flags the stream
+ * (FLIC_ST_UNDERRUN in status, which may be null) and copies nothing. */
+int flic_gather_words(const uint32_t* src, const int64_t* src_offsets, const int64_t* dst_starts,
+                      int64_t n_streams, uint32_t* dst, int64_t dst_capacity, int32_t* status,
+                      flic_cuda_stream_t stream);
 
 /* K5.  Replaces AdditiveCouple.forward / .backward's elementwise tail, couplelib.py:49-52 and
  * :58-60, with Round from roundlib.py:18-38:  x[:, a_ch:] += direction * Round_nbits(t), in place.

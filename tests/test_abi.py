@@ -21,7 +21,7 @@ def test_header_and_library_agree():
         assert hasattr(L, n), f"{n} declared in flic_b200.h but not exported"
     # the ctypes table binds exactly the declared functions
     assert sorted(_lib.SIGNATURES) == names
-    assert L.flic_abi_version() == 1
+    assert L.flic_abi_version() == 2
 
 
 def test_header_compiles_as_plain_c(tmp_path):

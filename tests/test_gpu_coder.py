@@ -389,3 +389,49 @@ def test_cta_per_stream_decoder_reports_what_the_lane_kernel_reports():
     assert st[1] == 0                      # the empty stream
     assert st[2] & _lib.ST_ZERO_SCALE and st[2] & _lib.ST_NONFINITE
     assert st[3] == 0
+
+
+# ---- chained streams: decode continuation ----------------------------------------------------------
+
+@pytest.mark.parametrize("n_streams", [1, 40, 5000])
+@pytest.mark.parametrize("kind", ["test", "edges"])
+def test_chained_levels_equal_one_stream_over_the_concatenation(oracle, kind, n_streams):
+    """coder.Encode (coder.py:18-27) carries the state from one level into the next.  Coding three
+    'levels' of every stream that way (init_states) and concatenating the words must give exactly
+    the stream that codes the three segments back to back in one go, and decoding it level by level,
+    last level first, each call continuing from the state and the unread words the previous one
+    stopped at (flic_rans_decode_resume), must return every level -- including when a level's first
+    symbol pushed a word, the case the reference's per-level buffers get wrong."""
+    from flic_b200 import rans
+    lens = [37, 64, 19]
+    n_levels = len(lens)
+    data = [gen(kind, n_streams * L, 100 + i) for i, L in enumerate(lens)]
+    dev = [_cuda(*d) for d in data]
+    offs = [torch.arange(n_streams + 1, device="cuda", dtype=torch.int64) * L for L in lens]
+    levels, carried = [], None
+    for (xd, md, sd), off in zip(dev, offs):
+        e = rans.encode_streams(xd, md, sd, off, init_states=carried, workspace=rans.Workspace(), own_output=False)
+        carried = e.final_states
+        levels.append(e)
+    chained = rans.chain_levels(levels)
+    assert not chained.status.any().item()
+    # the same symbols as one stream per image: [level 0 | level 1 | level 2] per stream
+    cat = [np.concatenate([d[k].reshape(n_streams, L) for d, L in zip(data, lens)], axis=1).reshape(-1) for k in range(3)]
+    total = sum(lens)
+    off_cat = np.arange(n_streams + 1, dtype=np.int64) * total
+    words_o, woff_o, states_o, _ = oracle.encode_streams(cat[0], cat[1], cat[2], off_cat, n_threads=8)
+    nw = chained.n_words()
+    assert np.array_equal(chained.word_offsets.cpu().numpy(), woff_o)
+    assert np.array_equal(_u32(chained.words)[:nw], words_o)
+    assert np.array_equal(_u64(chained.final_states), states_o)
+    # decode with continuation, both kernels
+    for which in (0, 1):
+        with _with_decode_kernel(which):
+            st, left = None, None
+            for lvl in reversed(range(n_levels)):
+                xd, md, sd = dev[lvl]
+                xr, st, status, left = rans.decode_streams(chained, md, sd, offs[lvl], check_end=lvl == 0, states=st,
+                                                           words_left=left, return_words_left=True)
+                assert not status.any().item()
+                assert torch.equal(xr, xd)
+            assert bool((st == (1 << 32)).all().item()) and not left.any().item()

@@ -166,7 +166,7 @@ def test_compress_decompress_lossless(oracle, n, codec_batch, sps):
     model = build_tiny().cuda()
     img = torch.randint(0, 256, (n, 3, 16, 16), dtype=torch.uint8, generator=torch.Generator().manual_seed(n)).cuda()
     stats = []
-    batch = model.compress(img, codec_batch=codec_batch, streams_per_segment=sps, stats=stats)
+    batch = model.compress(img, codec_batch=codec_batch, streams_per_segment=sps, stats=stats, chain_levels=False)
     blob = batch.to_bytes()
     rec = model.decompress(blob)
     assert torch.equal(rec, img)
@@ -194,6 +194,52 @@ def test_compress_decompress_lossless(oracle, n, codec_batch, sps):
     stream_bpd = 64 * batch.n_streams() / img.numel()
     assert real_bpd >= ideal_bpd - 1e-3
     assert real_bpd - stream_bpd <= ideal_bpd * 1.001 + 32 * batch.n_streams() / img.numel()
+
+
+@pytest.mark.parametrize("n,codec_batch", [(6, None), (5, 4), (1, 8), (9, 2)])
+def test_chained_streams_match_the_reference_coder_chained(oracle, n, codec_batch):
+    """The default partition: ONE stream per image whose state runs through all latent levels, as the
+    reference's coder.Encode chains it (coder.py:18-27: encode level 0, 1, ... each from the state
+    the previous one ended in, buffers appended).  Every image's (final state, words) must be what
+    the reference coder returns when called that way on the image's slices of (z, mean, scale); the
+    decoder continues each stream level by level, last level first (coder.py:29-38), and the cost
+    is 64 bits per IMAGE plus the words (trainer.py:326-327's formula with one stream per image)."""
+    model = build_tiny().cuda()
+    img = torch.randint(0, 256, (n, 3, 16, 16), dtype=torch.uint8, generator=torch.Generator().manual_seed(40 + n)).cuda()
+    stats = []
+    batch = model.compress(img, codec_batch=codec_batch, stats=stats)
+    assert batch.chained and batch.n_streams() == n
+    assert torch.equal(model.decompress(batch.to_bytes()), img)
+    assert torch.equal(model.decompress(batch), img)
+    cbs = batch.codec_batch
+    n_levels = model.nsplit
+    total_words = 0
+    for ci, chunk in enumerate(batch.sections):
+        assert len(chunk) == 1
+        enc = chunk[0]
+        n_real = min(cbs, n - ci * cbs)
+        words = enc.words.cpu().numpy().view(np.uint32)
+        woff = enc.word_offsets.cpu().numpy()
+        states = enc.final_states.cpu().numpy().view(np.uint64)
+        for b in range(n_real):
+            state, bufs = 1 << 32, []
+            for level in range(n_levels):
+                z, mean, logscale = stats[ci * n_levels + level]
+                seg = int(np.prod(model.latents_shape[level]))
+                sl = slice(b * seg, (b + 1) * seg)
+                scale = torch.exp(logscale.contiguous())
+                state, buf = oracle.encode(state, seg, z.reshape(-1)[sl].cpu().numpy(),
+                                           mean.contiguous().reshape(-1)[sl].cpu().numpy(), scale.reshape(-1)[sl].cpu().numpy())
+                bufs.append(buf)
+            want = np.concatenate(bufs) if bufs else np.zeros(0, np.uint32)
+            assert int(states[b]) == state
+            assert np.array_equal(words[woff[b]:woff[b + 1]], want)
+            total_words += want.size
+    assert batch.reference_bits() == 64 * n + 32 * total_words
+    # against one stream per image x level: the same words up to a few per image, 64 bits fewer per extra level
+    per_level = model.compress(img, codec_batch=codec_batch, chain_levels=False)
+    assert per_level.n_streams() == n * n_levels
+    assert batch.reference_bits() < per_level.reference_bits()
 
 
 def model_input(img):

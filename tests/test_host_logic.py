@@ -92,7 +92,7 @@ def test_container_round_trip_on_cpu():
                                         torch.zeros(chunk_imgs, dtype=torch.int32), 0))
         cb.sections.append(chunk)
     blob = cb.to_bytes()
-    assert len(blob) == 40 + sum(4 + 12 * e.n_streams + 4 * e.n_words() for ch in cb.sections for e in ch)
+    assert len(blob) == 44 + sum(4 + 12 * e.n_streams + 4 * e.n_words() for ch in cb.sections for e in ch)
     back = CompressedBatch.from_bytes(blob, "cpu")
     assert (back.n_images, back.shape, back.n_levels, back.codec_batch, back.model_tag) == (5, (3, 16, 16), 2, 4, 0xabcdef)
     for a, b in zip(cb.sections, back.sections):
@@ -104,6 +104,17 @@ def test_container_round_trip_on_cpu():
     for bad in (blob[:-1], blob + b"\0", b"XXXX" + blob[4:], blob[:30]):
         with pytest.raises(ValueError):
             CompressedBatch.from_bytes(bad, "cpu")
+    # version 1 (no flags word) is still read
+    v1 = blob[:4] + (1).to_bytes(2, "little") + blob[6:40] + blob[44:]
+    old = CompressedBatch.from_bytes(v1, "cpu")
+    assert not old.chained and old.n_words() == cb.n_words()
+    # chained: one section per chunk, every image one stream
+    ch = CompressedBatch(5, (3, 16, 16), 2, 4, 1, chained=True)
+    for chunk in cb.sections:
+        ch.sections.append(chunk[:1])
+    back = CompressedBatch.from_bytes(ch.to_bytes(), "cpu")
+    assert back.chained and [len(c) for c in back.sections] == [1, 1]
+    assert back.reference_bits() == 64 * 5 + 32 * sum(c[0].n_words() for c in cb.sections)
 
 
 def test_drop_in_argument_checks():
