@@ -57,6 +57,7 @@ SIGNATURES = {
     "flic_host_free": (None, [_vp]),
     "flic_codec_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i64)]),
     "flic_codec_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "flic_codec_probe_copies": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "flic_rans_encode_single": (C.c_int, [_vp, _u64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_u64),
                                           C.POINTER(C.c_int32)]),
     "flic_rans_decode_single": (C.c_int, [_vp, _u64, _vp, _i64, _i64, _vp, _vp, _vp, C.POINTER(_u64),

@@ -299,9 +299,11 @@ static void free_slots(flic_codec* c) {
     }
 }
 
+// Sizes are recorded only once every slot exists: after a failed (re)allocation the codec owns
+// nothing and reports a capacity of zero instead of sizes it does not have.
 static cudaError_t alloc_slots(flic_codec* c, int64_t ns, int64_t nt) {
-    c->slot_symbols = ns;
-    c->slot_streams = nt;
+    c->slot_symbols = 0;
+    c->slot_streams = 0;
     cudaError_t e = cudaSuccess;
     for (int i = 0; e == cudaSuccess && i < flic_codec::kSlots; ++i) {
         flic_codec::Slot& s = c->slot[i];
@@ -316,9 +318,15 @@ static cudaError_t alloc_slots(flic_codec* c, int64_t ns, int64_t nt) {
         if (e == cudaSuccess) e = cudaMalloc(&s.end_states, sizeof(uint64_t) * nt);
         if (e == cudaSuccess) e = cudaMalloc(&s.status, sizeof(int32_t) * nt);
         if (e == cudaSuccess) e = cudaMalloc(&s.workspace, (size_t)s.workspace_bytes);
-        if (e == cudaSuccess) e = cudaMallocHost(&s.h_word_offsets, sizeof(int64_t) * (nt + 1));
-        if (e == cudaSuccess) e = cudaMallocHost(&s.h_offsets, sizeof(int64_t) * (nt + 1));
+        if (e == cudaSuccess) e = cudaMallocHost(&s.h_word_offsets, sizeof(int64_t) * (nt + 8));
+        if (e == cudaSuccess) e = cudaMallocHost(&s.h_offsets, sizeof(int64_t) * (nt + 8));   // + scalars of the single-stream calls
     }
+    if (e != cudaSuccess) {
+        free_slots(c);
+        return e;
+    }
+    c->slot_symbols = ns;
+    c->slot_streams = nt;
     return e;
 }
 
@@ -346,8 +354,9 @@ static cudaError_t sync_all(flic_codec* c) {
 static int ensure_slot_symbols(flic_codec* c, int64_t symbols) {
     if (symbols <= c->slot_symbols) return 0;
     FLIC_CUDA(sync_all(c));
+    const int64_t streams = c->slot_streams > 0 ? c->slot_streams : (c->max_streams < (1 << 20) ? c->max_streams : (1 << 20));
     free_slots(c);
-    const cudaError_t e = alloc_slots(c, symbols, c->slot_streams);
+    const cudaError_t e = alloc_slots(c, symbols, streams);
     if (e != cudaSuccess) return cuda_fail(e, "growing codec slots");
     return 0;
 }
@@ -430,10 +439,10 @@ static int64_t chunk_cap(const flic_codec* c, int64_t chunk, int64_t done, int64
     return cap < c->slot_symbols ? cap : c->slot_symbols;
 }
 
-int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const float* scale,
-                      const int64_t* stream_offsets, int64_t n_streams, uint32_t* words_out,
-                      int64_t words_capacity, int64_t* word_offsets_out, uint64_t* states_out,
-                      int32_t* status_out, int64_t* n_words_out) {
+static int codec_encode_impl(flic_codec* c, const float* x, const float* mean, const float* scale,
+                             const int64_t* stream_offsets, int64_t n_streams, uint32_t* words_out,
+                             int64_t words_capacity, int64_t* word_offsets_out, uint64_t* states_out,
+                             int32_t* status_out, int64_t* n_words_out) {
     if (!c || n_streams < 0 || !stream_offsets || !word_offsets_out) return fail(FLIC_E_ARG, "bad argument");
     if (int rc = check_offsets(stream_offsets, n_streams)) return rc;
     const int64_t n_symbols = stream_offsets[n_streams];
@@ -514,10 +523,23 @@ int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const fl
     return 0;
 }
 
-int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_offsets,
-                      const uint64_t* states, const float* mean, const float* scale,
-                      const int64_t* stream_offsets, int64_t n_streams, float* x_out,
-                      uint64_t* end_states_out, int32_t* status_out) {
+// Whatever the outcome, nothing of the codec's is in flight when a host entry point returns: an
+// early return on an error would otherwise leave asynchronous copies writing into buffers the
+// caller is about to free.
+int flic_codec_encode(flic_codec* c, const float* x, const float* mean, const float* scale,
+                      const int64_t* stream_offsets, int64_t n_streams, uint32_t* words_out,
+                      int64_t words_capacity, int64_t* word_offsets_out, uint64_t* states_out,
+                      int32_t* status_out, int64_t* n_words_out) {
+    const int rc = codec_encode_impl(c, x, mean, scale, stream_offsets, n_streams, words_out, words_capacity,
+                                     word_offsets_out, states_out, status_out, n_words_out);
+    if (rc != 0 && c) sync_all(c);
+    return rc;
+}
+
+static int codec_decode_impl(flic_codec* c, const uint32_t* words, const int64_t* word_offsets,
+                             const uint64_t* states, const float* mean, const float* scale,
+                             const int64_t* stream_offsets, int64_t n_streams, float* x_out,
+                             uint64_t* end_states_out, int32_t* status_out) {
     if (!c || n_streams < 0 || !stream_offsets || !word_offsets) return fail(FLIC_E_ARG, "bad argument");
     if (n_streams == 0) return 0;
     if (int rc = check_offsets(stream_offsets, n_streams)) return rc;
@@ -576,6 +598,81 @@ int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_
     return 0;
 }
 
+int flic_codec_decode(flic_codec* c, const uint32_t* words, const int64_t* word_offsets,
+                      const uint64_t* states, const float* mean, const float* scale,
+                      const int64_t* stream_offsets, int64_t n_streams, float* x_out,
+                      uint64_t* end_states_out, int32_t* status_out) {
+    const int rc = codec_decode_impl(c, words, word_offsets, states, mean, scale, stream_offsets, n_streams, x_out,
+                                     end_states_out, status_out);
+    if (rc != 0 && c) sync_all(c);
+    return rc;
+}
+
+// The same copies as flic_codec_encode followed by flic_codec_decode -- same chunks, same three
+// streams, same host buffers -- with no kernel in between: what the host side of this box can
+// move for this call pattern, i.e. the ceiling the end-to-end number is measured against.
+// words / n_words stand for the compressed payload (copied down chunk by chunk in the encode
+// leg and up again in the decode leg, each chunk taking its share by symbol count).
+int flic_codec_probe_copies(flic_codec* c, const float* x, const float* mean, const float* scale,
+                            const int64_t* stream_offsets, int64_t n_streams, uint32_t* words,
+                            int64_t n_words, float* x_out) {
+    if (!c || n_streams < 0 || !stream_offsets) return fail(FLIC_E_ARG, "bad argument");
+    if (n_streams == 0) return 0;
+    if (int rc = check_offsets(stream_offsets, n_streams)) return rc;
+    const int64_t n_symbols = stream_offsets[n_streams];
+    if (n_symbols > c->max_symbols || n_streams > c->max_streams || n_words > n_symbols)
+        return fail(FLIC_E_CAPACITY, "codec sized for %lld symbols / %lld streams", (long long)c->max_symbols,
+                    (long long)c->max_streams);
+    if (n_symbols > 0 && (!x || !mean || !scale || !x_out || (n_words > 0 && !words))) return fail(FLIC_E_ARG, "null pointer");
+    FLIC_CUDA(cudaSetDevice(c->device));
+    const int64_t* off = stream_offsets;
+    auto leg = [&](bool decode) -> int {
+        int64_t s0 = 0, wdone = 0;
+        for (int64_t chunk = 0; s0 < n_streams; ++chunk) {
+            int64_t s1 = chunk_end(c, off, n_streams, s0, chunk_cap(c, chunk, off[s0], n_symbols));
+            if (s1 == s0) {
+                if (int rc = ensure_slot_symbols(c, off[s0 + 1] - off[s0])) return rc;
+                s1 = chunk_end(c, off, n_streams, s0, c->slot_symbols);
+            }
+            flic_codec::Slot& sl = c->slot[chunk % flic_codec::kSlots];
+            cudaStream_t st = c->streams[chunk % flic_codec::kSlots];
+            const int64_t a = off[s0], n = off[s1] - a, ns = s1 - s0;
+            const int64_t wend = n_symbols > 0 ? (int64_t)((double)n_words * (double)off[s1] / (double)n_symbols) : 0;
+            const int64_t nw = wend - wdone;
+            if (!decode) {
+                if (n > 0) {
+                    FLIC_CUDA(cudaMemcpyAsync(sl.x, x + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+                    FLIC_CUDA(cudaMemcpyAsync(sl.mean, mean + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+                    FLIC_CUDA(cudaMemcpyAsync(sl.scale, scale + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+                }
+                FLIC_CUDA(cudaMemcpyAsync(sl.offsets, sl.h_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+                FLIC_CUDA(cudaMemcpyAsync(sl.h_word_offsets, sl.word_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyDeviceToHost, st));
+                if (nw > 0) FLIC_CUDA(cudaMemcpyAsync(words + wdone, sl.packed, sizeof(uint32_t) * nw, cudaMemcpyDeviceToHost, st));
+            } else {
+                if (nw > 0) FLIC_CUDA(cudaMemcpyAsync(sl.packed, words + wdone, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, st));
+                FLIC_CUDA(cudaMemcpyAsync(sl.word_offsets, sl.h_word_offsets, sizeof(int64_t) * (ns + 1), cudaMemcpyHostToDevice, st));
+                if (n > 0) {
+                    FLIC_CUDA(cudaMemcpyAsync(sl.mean, mean + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+                    FLIC_CUDA(cudaMemcpyAsync(sl.scale, scale + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+                    FLIC_CUDA(cudaMemcpyAsync(x_out + a, sl.x, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+                }
+            }
+            wdone = wend;
+            s0 = s1;
+        }
+        FLIC_CUDA(sync_all(c));
+        return 0;
+    };
+    int rc = leg(false);
+    if (rc == 0) rc = leg(true);
+    if (rc != 0) sync_all(c);
+    return rc;
+}
+
+// One stream, the reference's own signatures.  Inputs go up from the caller's (usually pageable)
+// arrays, the small outputs and the worst-case word buffer come down in the same batch, and the
+// call synchronises once: scalars that have to outlive the enqueue sit in the slot's pinned
+// staging arrays, not on this stack frame.
 int flic_rans_encode_single(flic_codec* c, uint64_t state, int64_t n, const float* x,
                             const float* mean, const float* scale, uint32_t* buffer_out,
                             int64_t* n_words_out, uint64_t* state_out, int32_t* status_out) {
@@ -590,28 +687,35 @@ int flic_rans_encode_single(flic_codec* c, uint64_t state, int64_t n, const floa
     if (int rc = ensure_slot_symbols(c, n)) return rc;
     flic_codec::Slot& s = c->slot[0];
     cudaStream_t st = c->streams[0];
-    const int64_t offs[2] = {0, n};
-    int64_t woffs[2] = {0, 0};
-    int32_t status = 0;
-    FLIC_CUDA(cudaMemcpyAsync(s.x, x, sizeof(float) * n, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.mean, mean, sizeof(float) * n, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.scale, scale, sizeof(float) * n, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.offsets, offs, sizeof offs, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaMemcpyAsync(s.end_states, &state, sizeof state, cudaMemcpyHostToDevice, st));
-    FLIC_CUDA(cudaStreamSynchronize(st));  // offs / state live on this stack frame
-    if (int rc = flic_rans_encode(s.x, s.mean, s.scale, s.offsets, 1, n, s.end_states, s.workspace,
-                                  s.workspace_bytes, s.packed, n, s.word_offsets, s.states, s.status, st))
-        return rc;
-    FLIC_CUDA(cudaMemcpyAsync(woffs, s.word_offsets, sizeof woffs, cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaMemcpyAsync(state_out, s.states, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaMemcpyAsync(&status, s.status, sizeof status, cudaMemcpyDeviceToHost, st));
-    FLIC_CUDA(cudaStreamSynchronize(st));
-    *n_words_out = woffs[1];
+    if (s.busy) FLIC_CUDA(cudaEventSynchronize(c->done[0]));
+    s.busy = false;
+    // pinned staging: h_offsets = {0, n, state, status}, h_word_offsets = {0, n_words}
+    s.h_offsets[0] = 0;
+    s.h_offsets[1] = n;
+    s.h_offsets[2] = (int64_t)state;
+    int rc = 0;
+    cudaError_t e = cudaMemcpyAsync(s.x, x, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.mean, mean, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.scale, scale, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.offsets, s.h_offsets, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.end_states, s.h_offsets + 2, sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        rc = flic_rans_encode(s.x, s.mean, s.scale, s.offsets, 1, n, s.end_states, s.workspace, s.workspace_bytes,
+                              s.packed, n, s.word_offsets, s.states, s.status, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(s.h_word_offsets, s.word_offsets, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(s.h_offsets + 2, s.states, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(s.h_offsets + 3, s.status, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    // a stream emits at most one word per symbol: the whole worst-case buffer comes down with the rest
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(buffer_out, s.packed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) return cuda_fail(e, "flic_rans_encode_single");
+    if (rc) return rc;
+    int32_t status;
+    memcpy(&status, s.h_offsets + 3, sizeof status);
+    *n_words_out = s.h_word_offsets[1];
+    *state_out = (uint64_t)s.h_offsets[2];
     if (status_out) *status_out = status;
-    if (woffs[1] > 0) {
-        FLIC_CUDA(cudaMemcpyAsync(buffer_out, s.packed, sizeof(uint32_t) * woffs[1], cudaMemcpyDeviceToHost, st));
-        FLIC_CUDA(cudaStreamSynchronize(st));
-    }
     if (status) return fail(FLIC_E_STATUS, "stream status 0x%x", status);
     return 0;
 }
@@ -628,41 +732,49 @@ int flic_rans_decode_single(flic_codec* c, uint64_t state, const uint32_t* buffe
     if (n == 0) return 0;
     if (!mean_reversed || !scale_reversed || !message_out || (n_buffer > 0 && !buffer_reversed))
         return fail(FLIC_E_ARG, "null pointer");
-    // Undo the caller's reversal (trainer.py:317) on the host; the kernel walks streams backwards.
-    float* fm = (float*)malloc(sizeof(float) * (size_t)n * 2);
-    uint32_t* fb = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n_buffer > 0 ? n_buffer : 1));
-    if (!fm || !fb) { free(fm); free(fb); return fail(FLIC_E_NOMEM, "out of host memory"); }
-    float* fs = fm + n;
-    for (int64_t i = 0; i < n; ++i) { fm[i] = mean_reversed[n - 1 - i]; fs[i] = scale_reversed[n - 1 - i]; }
-    for (int64_t i = 0; i < n_buffer; ++i) fb[i] = buffer_reversed[n_buffer - 1 - i];
-    const int64_t offs[2] = {0, n};
-    const int64_t woffs[2] = {0, n_buffer};
-    int32_t status = 0;
-    int rc = 0;
-    cudaError_t e = cudaSetDevice(c->device);
-    if (e == cudaSuccess && ensure_slot_symbols(c, n > n_buffer ? n : n_buffer) != 0) { free(fm); free(fb); return FLIC_E_NOMEM; }
+    FLIC_CUDA(cudaSetDevice(c->device));
+    if (int rc = ensure_slot_symbols(c, n > n_buffer ? n : n_buffer)) return rc;
     flic_codec::Slot& s = c->slot[0];
     cudaStream_t st = c->streams[0];
-    if (e == cudaSuccess && n_buffer > 0) e = cudaMemcpyAsync(s.packed, fb, sizeof(uint32_t) * n_buffer, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.mean, fm, sizeof(float) * n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.scale, fs, sizeof(float) * n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.offsets, offs, sizeof offs, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.word_offsets, woffs, sizeof woffs, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.states, &state, sizeof state, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (s.busy) FLIC_CUDA(cudaEventSynchronize(c->done[0]));
+    s.busy = false;
+    // The caller's reversal (trainer.py:317) is undone on the device: the arrays go up as they are
+    // and three small kernels reverse them (the decode kernels walk a stream from its end).
+    s.h_offsets[0] = 0;
+    s.h_offsets[1] = n;
+    s.h_offsets[2] = (int64_t)state;
+    s.h_word_offsets[0] = 0;
+    s.h_word_offsets[1] = n_buffer;
+    int rc = 0;
+    float* const up = (float*)s.workspace;                 // n floats of upload space (the encode scratch is idle)
+    cudaError_t e = cudaSuccess;
+    if (n_buffer > 0) {
+        e = cudaMemcpyAsync(up, buffer_reversed, sizeof(uint32_t) * n_buffer, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = flic::launch_reverse_u32((const uint32_t*)up, s.packed, n_buffer, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.x, mean_reversed, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = flic::launch_reverse_u32((const uint32_t*)s.x, (uint32_t*)s.mean, n, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.x, scale_reversed, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = flic::launch_reverse_u32((const uint32_t*)s.x, (uint32_t*)s.scale, n, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.offsets, s.h_offsets, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.word_offsets, s.h_word_offsets, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.states, s.h_offsets + 2, sizeof(uint64_t), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
         rc = flic_rans_decode(s.packed, s.word_offsets, s.states, s.mean, s.scale, s.offsets, 1, s.x, s.end_states,
                               s.status, 0, st);
-    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(fm, s.x, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(state_out, s.end_states, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(&status, s.status, sizeof status, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess && rc == 0)
-        for (int64_t i = 0; i < n; ++i) message_out[i] = fm[n - 1 - i];
-    free(fm);
-    free(fb);
+    // the message goes back reversed, as the reference returns it
+    if (e == cudaSuccess && rc == 0) e = flic::launch_reverse_u32((const uint32_t*)s.x, (uint32_t*)up, n, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(message_out, up, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(s.h_offsets + 2, s.end_states, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(s.h_offsets + 3, s.status, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return cuda_fail(e, "flic_rans_decode_single");
     if (rc) return rc;
+    g_launches += 4;
+    int32_t status;
+    memcpy(&status, s.h_offsets + 3, sizeof status);
+    *state_out = (uint64_t)s.h_offsets[2];
     if (status_out) *status_out = status;
     if (status) return fail(FLIC_E_STATUS, "stream status 0x%x", status);
     return 0;

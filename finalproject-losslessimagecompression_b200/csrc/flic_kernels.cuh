@@ -41,6 +41,9 @@ cudaError_t launch_gather_words(const uint32_t* src, const int64_t* src_offsets,
                                 int64_t n_streams, uint32_t* dst, int64_t dst_capacity, int32_t* status,
                                 cudaStream_t stream);
 
+// dst[i] = src[n - 1 - i] (32-bit elements; src != dst)
+cudaError_t launch_reverse_u32(const uint32_t* src, uint32_t* dst, int64_t n, cudaStream_t stream);
+
 // K4: exclusive scan of counts -> word_offsets[n_streams + 1]; gather scratch -> packed.
 // scan_tmp needs scan_tmp_elems(n_streams) int64 elements.
 int64_t scan_tmp_elems(int64_t n_streams);

@@ -57,6 +57,17 @@ dlogistic_log_prob_kernel(const float* __restrict__ x, const float* __restrict__
     }
 }
 
+// Elementwise only (no sums wanted): grid-stride over every element, so that the whole GPU works
+// on one tensor (the per-image kernel above would put it on one SM).
+__global__ void __launch_bounds__(256)
+dlogistic_log_prob_elementwise_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                      const float* __restrict__ logscale, int64_t n, float half_bin, float eps,
+                                      float* __restrict__ logp_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        logp_out[i] = dlogistic_log_prob(__ldg(x + i), __ldg(mean + i), __ldg(logscale + i), half_bin, eps);
+}
+
 __global__ void __launch_bounds__(256)
 dlogistic_sample_kernel(const float* __restrict__ u, const float* __restrict__ mean,
                         const float* __restrict__ logscale, int64_t n, float bins, float inv_bins,
@@ -77,6 +88,16 @@ cudaError_t launch_dlogistic_log_prob(const float* x, const float* mean, const f
                                       float* logp_out, float* sum_out, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     const float half_bin = 0.5f / (float)(1 << nbits);
+    if (!sum_out) {
+        const int64_t n = batch * per_item;
+        if (n <= 0) return cudaSuccess;
+        int64_t blocks = (n + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        dlogistic_log_prob_elementwise_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, mean, logscale, n, half_bin, eps,
+                                                                                  logp_out);
+        return cudaGetLastError();
+    }
     dlogistic_log_prob_kernel<<<(unsigned)batch, 256, 0, stream>>>(x, mean, logscale, per_item, half_bin, eps,
                                                                   logp_out, sum_out);
     return cudaGetLastError();

@@ -160,4 +160,21 @@ cudaError_t launch_gather_words(const uint32_t* src, const int64_t* src_offsets,
     return cudaGetLastError();
 }
 
+// dst[i] = src[n - 1 - i]: the reference's callers hand decode() its arrays reversed and get the
+// message back reversed (trainer.py:317-318); the single-stream drop-in undoes that on the device.
+__global__ void __launch_bounds__(256)
+reverse_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[n - 1 - i];
+}
+
+cudaError_t launch_reverse_u32(const uint32_t* src, uint32_t* dst, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    reverse_u32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, n);
+    return cudaGetLastError();
+}
+
 }  // namespace flic

@@ -213,6 +213,14 @@ int flic_codec_decode(flic_codec* codec, const uint32_t* words, const int64_t* w
                       const int64_t* stream_offsets, int64_t n_streams, float* x_out,
                       uint64_t* end_states_out, int32_t* status_out);
 
+/* Measurement aid: the host<->device copies of flic_codec_encode followed by flic_codec_decode for
+ * these buffers -- same chunks, same three CUDA streams -- with no kernel in between.  What the
+ * host side of a box can move for this call pattern is the ceiling of the end-to-end number
+ * (bench.py reports both).  words / n_words stand for the compressed payload. */
+int flic_codec_probe_copies(flic_codec* codec, const float* x, const float* mean, const float* scale,
+                            const int64_t* stream_offsets, int64_t n_streams, uint32_t* words,
+                            int64_t n_words, float* x_out);
+
 /* Exact argument-for-argument drop-ins for the reference's two functions (single stream,
  * caller-supplied state), HOST memory:
  *   encode(state, n, x_, mean_, scale_) -> (state, buffer)             rans/rans.pyx:37

@@ -662,3 +662,31 @@ def test_twolevel_flows_compress_decompress(oracle):
     assert real_bpd >= bpd - 1e-3 and real_bpd < bpd * 1.02 + 64 * (3 + 3 * 621) / img.numel() + 0.05
     with pytest.raises(ValueError):
         model.decompress(b"XXXX" + blob[4:])
+
+
+def test_reference_import_lines_resolve_to_the_cuda_coder(oracle):
+    """compat/ on PYTHONPATH makes `from rans.rans import encode, decode` (trainer.py:32, coder.py:15)
+    and `from rans import encode, decode` (rans/test.py:1) resolve, unmodified, to this repository's
+    coder.  The reference's two self-tests (rans/test.py:6-36 with n patched down, coder.py:41-73),
+    restated in tests/ref_style_selftest.py, run as a FILE in a fresh interpreter: no errors, final
+    state 1<<32, and state / word count / SHA-256 of the words equal what the reference's own coder
+    produced for the same lists (tests/golden/kat_random.json, made by tests/golden/make_golden.py)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {**os.environ, "PYTHONPATH": os.path.join(root, "compat")}
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "ref_style_selftest.py"), "200000", "100000"],
+                         capture_output=True, text=True, env=env, cwd=root, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("rans_test_py", "coder_py_main"):
+        r = res[key]
+        assert r["errors"] == 0 and r["final_state"] == 1 << 32
+        assert r["list_types"] == ["list", "list", "int", "float"]
+    # the lists are built exactly as tests/golden/make_golden.py built them for the reference's coder
+    kat = json.load(open(os.path.join(root, "tests", "golden", "kat_random.json")))
+    for key, gold in (("rans_test_py", kat["200000"]), ("coder_py_main", kat["coder_100000"])):
+        assert res[key]["state"] == gold["state"]
+        assert res[key]["words"] == gold["n_words"] and res[key]["sha256"] == gold["sha256"]
