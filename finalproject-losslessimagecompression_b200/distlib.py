@@ -57,6 +57,11 @@ class DLogistic(nn.Module):
 
     @staticmethod
     def _log_prob_torch(x, mean, logscale, nbits=8, eps=1e-8):
+        """The formula of distlib.py:40-55 as differentiable torch ops.  Kept on purpose, for one
+        caller only: a training loop that needs d(log_prob)/d(params) (loading a reference
+        checkpoint and fine-tuning it must keep working).  It is NOT a second backend of the coding
+        path: compress / decompress / log_likelihood run under torch.no_grad() and always take the
+        CUDA kernel; CPU tensors raise (`_fused_ok`), they never come here."""
         scale = torch.exp(logscale)
         half = 0.5 / (2 ** nbits)
         up = F.logsigmoid((x + half - mean) / scale)

@@ -435,3 +435,28 @@ def test_chained_levels_equal_one_stream_over_the_concatenation(oracle, kind, n_
                 assert not status.any().item()
                 assert torch.equal(xr, xd)
             assert bool((st == (1 << 32)).all().item()) and not left.any().item()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_equals_the_reference_build_on_this_box(oracle, kind):
+    """The checker itself, on the box whose libm defines expf for the run: the C restatement
+    (oracle/liboracle.so) against the reference's own rans.pyx rebuilt into oracle/_ref (which
+    travels here with the repository), same inputs, bit for bit -- the comparison
+    tests/test_oracle_pinning.py makes in the build container, repeated where the GPU results are
+    judged against the oracle."""
+    ref = oracle.ref_rans()
+    if ref is None:
+        pytest.skip("oracle/_ref was not shipped; the committed goldens pin the oracle instead")
+    n = 60_000
+    x, mean, scale = gen(kind, n, 21)
+    xl, ml, sl = x.tolist(), mean.tolist(), scale.tolist()
+    state_r, buf_r = ref.encode(1 << 32, n, xl, ml, sl)
+    state_o, buf_o = oracle.encode(1 << 32, n, x, mean, scale)
+    assert state_r == state_o and buf_r == buf_o.tolist()
+    end_r, msg_r = ref.decode(state_r, buf_r[::-1], n, ml[::-1], sl[::-1])
+    assert end_r == 1 << 32 and msg_r[::-1] == xl
+    # and the CUDA coder against the reference build directly
+    from flic_b200 import rans
+    xd, md, sd = _cuda(x, mean, scale)
+    enc = rans.encode_streams(xd, md, sd)
+    assert int(_u64(enc.final_states)[0]) == state_r and _u32(enc.words).tolist() == buf_r

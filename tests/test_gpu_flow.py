@@ -690,3 +690,31 @@ def test_reference_import_lines_resolve_to_the_cuda_coder(oracle):
     for key, gold in (("rans_test_py", kat["200000"]), ("coder_py_main", kat["coder_100000"])):
         assert res[key]["state"] == gold["state"]
         assert res[key]["words"] == gold["n_words"] and res[key]["sha256"] == gold["sha256"]
+
+
+def test_full_width_imagenet64_model_round_trip():
+    """configs/imagenet64.yaml at its real width (growth 512, depth 12, 8 flows x 3 levels, 60 M
+    parameters) on one codec batch of 64 images: compress -> bytes -> decompress must return the
+    pixels, i.e. the convolutions of the two passes (cuDNN, deterministic, TF32 off) agree bit for
+    bit on every one of the 786 432 latents' parameters.  (The reduced-width models of the other
+    tests exercise the same code with far fewer accumulations per output.)"""
+    import random
+    from flic_b200 import flows
+    layer = dict(name="DenseLayer", act="ReLU")
+    block = dict(name="DenseBlock", growth_channel=512, depth=12, layer=layer)
+    cfg = dict(name="IDFlows", nflows=8, nbits=8, nsplit=3, H=64, W=64, C=3,
+               couple=dict(name="AdditiveCouple", split=0.75, nn=block, round=dict(name="Round", nbits=8)),
+               extenddim=dict(name="ExtendDim", scale=2),
+               prior=dict(name="Prior", round=dict(name="Round", nbits=8), nn=block),
+               distribution=dict(name="DLogistic"), round=dict(name="Round", nbits=8))
+    torch.manual_seed(0)
+    random.seed(0)
+    model = flows.build_model(cfg)
+    flows.perturb_heads(model, 0.02)
+    model = model.cuda().eval()
+    img = torch.randint(0, 256, (64 + 7, 3, 64, 64), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).cuda()
+    batch = model.compress(img, codec_batch=64)          # a full chunk and a padded one
+    assert batch.chained and batch.n_streams() == 71
+    blob = batch.to_bytes()
+    assert torch.equal(model.decompress(blob), img)
+    assert 9.5 < 8 * len(blob) / img.numel() < 10.8      # random-init model on uniform noise: ~10.1 bits/dim
