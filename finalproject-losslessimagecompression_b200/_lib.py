@@ -34,6 +34,7 @@ SIGNATURES = {
     "flic_kernel_launches": (_i64, []),
     "flic_last_coder_kernel": (C.c_char_p, [C.c_int]),
     "flic_set_decode_kernel": (C.c_int, [C.c_int]),
+    "flic_decode_cluster_capacity": (_i64, [C.c_int]),
     "flic_cdf_tables": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flic_debug_expf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "flic_debug_part1": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -71,7 +71,11 @@ int flic_abi_version(void) { return FLIC_ABI_VERSION; }
 const char* flic_last_error(void) { return g_err; }
 int64_t flic_kernel_launches(void) { return g_launches.load(); }
 const char* flic_last_coder_kernel(int which) { return flic::last_coder_kernel(which); }
-int flic_set_decode_kernel(int which) { return flic::set_decode_kernel(which < -1 || which > 1 ? -1 : which); }
+int64_t flic_decode_cluster_capacity(int cluster) { return flic::coop_cluster_capacity(cluster); }
+int flic_set_decode_kernel(int which) {
+    const bool known = which == -1 || which == 0 || which == 1 || which == 2 || which == 4 || which == 8;
+    return flic::set_decode_kernel(known ? which : -1);
+}
 
 int flic_cdf_tables(const float* x, const float* mean, const float* scale, int64_t n_symbols,
                     uint32_t* start, uint32_t* freq, int32_t* status_word,

@@ -226,8 +226,12 @@ FLIC_HD int d2i_rz(double v) {
 // exact.  M's significand is even in those ulps, so ties break exactly as the conversion's do.
 // Differences from the conversion pair: no overflow to inf and no subnormal range.  Callers show
 // that both only occur where part1 is saturated anyway (see part1_at).
+// M's low word only has to be even in units of its last place for the ties to break as the
+// conversion's do, and small enough to leave v + M in M's binade; taking the exponent field itself
+// (bits 20..30 only: even, and below 2^-21 relative) saves the move that would zero a register.
 FLIC_HD double round24(double v) {
-    const double M = f64_from_words((f64_hi(v) & 0x7ff00000u) + 0x01d80000u, 0u);
+    const uint32_t ex = f64_hi(v) & 0x7ff00000u;
+    const double M = f64_from_words(ex + 0x01d80000u, ex);
     return dsub(dadd(v, M), M);
 }
 
@@ -363,7 +367,25 @@ FLIC_HD int lower_of_d(double mean_d) {
     const int n = (int)floor_nonneg_u32(dadd(fabs(v), 0.5));
     return (int64_t)f64_bits(v) < 0 ? -n : n;
 }
-FLIC_HD int lower_of(float mean) { return lower_of_d((double)mean); }
+// The same integer on the float pipe.  m = 256 mean is exact in float (a power-of-two scaling;
+// |mean| <= 16384 keeps it below 2^22), and with v = m - 1024:
+//   v >= 0:  round(v) = floor(m + 0.5) - 1024
+//   v <  0:  round(v) = ceil(m - 0.5) - 1024 = -floor(-m + 0.5) - 1024        (half away from zero)
+// floor(w + 0.5) is taken from a round-DOWN add: RD(w + 0.5) lies between floor(w + 0.5) -- an
+// integer below 2^23, hence a float, and not above the exact sum -- and the exact sum, so its floor
+// is the exact sum's.  Three FP64 operations and two constant moves less per symbol than lower_of_d.
+FLIC_HD int lower_of(float mean) {
+    const float m = mean * 256.0f;
+    const bool neg = m < 1024.0f;
+    const float w = neg ? -m : m;
+#if defined(__CUDA_ARCH__)
+    const int t = __float2int_rd(__fadd_rd(w, 0.5f));
+#else
+    const double td = floor((double)w + 0.5);
+    const int t = td >= 2147483648.0 ? 2147483647 : (td <= -2147483648.0 ? (-2147483647 - 1) : (int)td);   // NaN / inf: any value, the stream is flagged
+#endif
+    return (neg ? -t : t) - 1024;
+}
 
 struct SymbolModel {
     double mean_d;   // (double)mean
@@ -415,7 +437,7 @@ FLIC_HD SymbolModel make_model(float mean, float scale) {
     m.mean_d = (double)mean;
     m.scale_d = (double)scale;
     m.rscale = rcp_cubic(m.scale_d);
-    m.lower = lower_of_d(m.mean_d);
+    m.lower = lower_of(mean);
     return m;
 }
 
@@ -585,12 +607,16 @@ FLIC_HD double rcp_biased_low(double a) {
 // less than 2^-8 below it (relative errors: bias 2^-49, state_d 2^-53, rf 2^-52, product 2^-53;
 // times q < 2^40), so floor(qd) is q or q - 1 and one integer correction makes it exact.
 // The remainder fits 32 bits, so it is computed modulo 2^32.
-FLIC_HD bool rans_push(uint64_t& state, uint32_t start, uint32_t freq, uint32_t& word) {
+FLIC_HD double push_reciprocal(uint32_t freq) { return rcp_biased_low(u32_to_f64(freq)); }
+
+// rf = push_reciprocal(freq): it does not depend on the state, so a caller whose table entries are
+// produced ahead of the serial recurrence (the producer / consumer encoder) has the producers
+// compute it, which leaves convert -> multiply -> fix-up on the chain.
+FLIC_HD bool rans_push_rf(uint64_t& state, uint32_t start, uint32_t freq, double rf, uint32_t& word) {
     uint32_t hi = (uint32_t)(state >> 32), lo = (uint32_t)state;
     // state >= freq << 40: the threshold's low 32 bits are zero, so only the high words compare
     const bool emit = hi >= (freq << 8);
     if (emit) { word = lo; lo = hi; hi = 0; }
-    const double rf = rcp_biased_low(u32_to_f64(freq));
     const double qd = dmul(u64_to_f64(hi, lo), rf);
 #if defined(__CUDA_ARCH__)
     const uint64_t qb = (uint64_t)__double_as_longlong(__dadd_rz(qd, 4503599627370496.0));  // 2^52 + floor(qd)
@@ -605,6 +631,9 @@ FLIC_HD bool rans_push(uint64_t& state, uint32_t start, uint32_t freq, uint32_t&
     const uint64_t add = (uint64_t)(rem + start) + (up ? (uint64_t)(0x1000000u - freq) : 0ull);
     state = (qb << 24) + add;
     return emit;
+}
+FLIC_HD bool rans_push(uint64_t& state, uint32_t start, uint32_t freq, uint32_t& word) {
+    return rans_push_rf(state, start, freq, push_reciprocal(freq), word);
 }
 
 // Decoder: state update after the symbol is known (rans.pyx:108).
@@ -634,16 +663,14 @@ FLIC_HD void rans_pop32(uint32_t& hi, uint32_t& lo, uint32_t start, uint32_t fre
 FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
     const float m = mean * 256.0f;
     const float c = scale * 256.0f;
-    const int mi = (int)mod;
-    // Q = A + 1024 - mod = (mod ^ 0xffffff) - 1023 for mod < 2^24 (no constant register needed)
-    int P = mi - 1024, Q = (int)(mod ^ 0xffffffu) - 1023;
-    P = P < 2 ? 2 : P;
-    Q = Q < 2 ? 2 : Q;
-    // A sig(u0) - mod is -1024 unless a tail clamp moved P or Q, i.e. for 2 x 1026 of the 2^24
-    // values of mod; there the guess is just less sharp (the bracket search takes over)
+    // P = mod - 1024, Q = A - P.  Neither is kept positive in the tails (mod < 1025 or
+    // mod > A + 1023: 1.2e-4 of all slots) and the guess is not limited to the window: whatever comes
+    // out there -- a wrapped integer, a NaN turned into an arbitrary index -- fails the caller's test
+    // (in-window and CDF(g - 1) <= mod < CDF(g)) and the bracket search takes over.
+    const uint32_t P = mod - 1024u, Q = 16776192u - mod;
     const float Pf = (float)P, Qf = (float)Q;
 #if defined(__CUDA_ARCH__)
-    float lp, lq;   // P, Q >= 2 are normal floats: the flush-to-zero forms skip the subnormal fix-ups
+    float lp, lq;   // flush-to-zero forms: no subnormal fix-ups (P, Q are integers)
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(Pf));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lq) : "f"(Qf));
     const float u0 = (lp - lq) * 0.693147181f;
@@ -657,18 +684,21 @@ FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdh) : "f"(dh));
     const float u1 = ffma(-h, rdh, u0);
     // ceil through a round-up add of 1.5 * 2^23 (exact integer in the low mantissa bits when
-    // |sr| < 2^22; anything else is clamped into the window below)
+    // |sr| < 2^22; anything else lands outside the window)
     const float sr = ffma(c, u1, m - 0.5f);
-    int g = (int)(__float_as_uint(__fadd_ru(sr, 12582912.0f)) - 0x4b400000u);
+    return (int)(__float_as_uint(__fadd_ru(sr, 12582912.0f)) - 0x4b400000u);
 #else
     const float u1 = ffma(-h, 1.0f / dh, u0);
     const float sr = ceilf(ffma(c, u1, m - 0.5f));
-    int g = lower + 1024;
-    if (fabsf(sr) < 4.0e6f) g = (int)sr;
+    return fabsf(sr) < 4.0e6f ? (int)sr : lower - 1;   // NaN too: outside the window
 #endif
+}
+
+// A guess is usable when it lies in the window; the callers test that together with the CDF pair.
+FLIC_HD bool guess_in_window(int g, int lower) { return (uint32_t)(g - lower) < (uint32_t)kWindow; }
+FLIC_HD int clamp_to_window(int g, int lower) {
     g = g < lower ? lower : g;
-    g = g > lower + (kWindow - 1) ? lower + (kWindow - 1) : g;
-    return g;
+    return g > lower + (kWindow - 1) ? lower + (kWindow - 1) : g;
 }
 
 // Bracketing search.  Invariant: CDF(lo) <= mod < CDF(hi), where lo = lower-1 and
@@ -693,7 +723,7 @@ FLIC_HD SearchState search_begin(uint32_t mod, float mean, float scale, const Sy
     st.c_hi = -1;
     st.step = 1;
     st.done = false;
-    st.probe = guess_symbol(mod, mean, scale, m.lower);
+    st.probe = clamp_to_window(guess_symbol(mod, mean, scale, m.lower), m.lower);
     return st;
 }
 
@@ -733,7 +763,7 @@ FLIC_HD int decode_symbol(uint64_t& state, float mean, float scale,
     const uint32_t mod = (uint32_t)state & kProbMask;
     const SymbolModel m = make_model(mean, scale);
     if (!params_ok(mean, scale)) flags |= param_flags(mean, scale);
-    const int g = guess_symbol(mod, mean, scale, m.lower);
+    const int g = clamp_to_window(guess_symbol(mod, mean, scale, m.lower), m.lower);
     int c_lo, c_hi;
     cdf_pair(g, m, s_tab, c_lo, c_hi);
     int s = g;
@@ -786,7 +816,9 @@ SymbolHit decode_symbol_search(uint32_t mod, float mean, float scale, ExpTab tab
     SearchState st;
     st.lo = m.lower - 1; st.hi = m.lower + kWindow;
     st.c_lo = -1; st.c_hi = -1; st.step = 2; st.done = false;
-    if (c_hi <= (int)mod) {  // answer is right of g
+    if (!guess_in_window(g, m.lower)) {   // nothing is known yet: start from the nearest window end
+        st.probe = clamp_to_window(g, m.lower);
+    } else if (c_hi <= (int)mod) {  // answer is right of g
         st.lo = g; st.c_lo = c_hi;
         st.probe = g + 1 < st.hi ? g + 1 : st.hi;
     } else {                 // c_lo > mod and g - 1 >= lower: answer is at or left of g - 1
@@ -813,7 +845,7 @@ FLIC_HD int decode_symbol_model(uint32_t& hi, uint32_t& lo, float mean, float sc
     cdf_pair(g, m, tab, c_lo, c_hi);
     int s = g;
     const bool left_ok = (g == m.lower) || (c_lo <= (int)mod);  // window's left edge is virtual
-    if (!(left_ok && c_hi > (int)mod)) {
+    if (!(left_ok && c_hi > (int)mod && guess_in_window(g, m.lower))) {
         const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
@@ -832,7 +864,7 @@ FLIC_HD int decode_symbol_lean(uint32_t& hi, uint32_t& lo, float mean, float sca
     cdf_pair(g, m, tab, c_lo, c_hi);
     int s = g;
     const bool left_ok = (g == m.lower) || (c_lo <= (int)mod);  // window's left edge is virtual
-    if (!(left_ok && c_hi > (int)mod)) {
+    if (!(left_ok && c_hi > (int)mod && guess_in_window(g, m.lower))) {
         const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;

@@ -15,7 +15,8 @@ constexpr int kCoderWarps = 4;  // warps per CTA in encode/decode kernels
 // Name of the coder kernel the last launch_rans_encode (which = 0) / launch_rans_decode (1) chose.
 const char* last_coder_kernel(int which);
 void note_coder_kernel(int which, const char* name);
-// Decode kernel choice: -1 by stream count, 0 lane-per-stream, 1 CTA-per-stream.  Returns the old value.
+// Decode kernel choice: -1 by stream count, 0 lane-per-stream, 1 CTA-per-stream, 2 / 4 / 8 a cluster of
+// that many CTAs per stream.  Returns the old value.
 int set_decode_kernel(int which);
 
 // K1  (x, mean, scale) -> (start, freq)                     rans/rans.pyx:49-56
@@ -68,13 +69,16 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
                                uint64_t* end_states, int32_t* status, int check_end,
                                WordsLeft left, cudaStream_t stream);
 
-// K3c: the same for few streams -- one CTA per stream, exact CDF windows tabulated ahead of the
-// serial chain by producer warps (rans_decode_coop.cu).  launch_rans_decode picks it by stream count.
+// K3c / K3d: the same for few streams -- one CTA (cluster = 1) or one thread-block cluster of 2, 4
+// or 8 CTAs per stream, exact CDF windows tabulated ahead of the serial chain by producer warps
+// (rans_decode_coop.cu).  launch_rans_decode picks kernel and cluster size by stream count.
 cudaError_t launch_rans_decode_coop(const uint32_t* packed, const int64_t* word_offsets,
                                     const uint64_t* states, const float* mean, const float* scale,
                                     const int64_t* offsets, int64_t n_streams, float* x_out,
                                     uint64_t* end_states, int32_t* status, int check_end,
-                                    WordsLeft left, cudaStream_t stream);
+                                    WordsLeft left, int cluster, cudaStream_t stream);
+// Clusters of `cluster` (2, 4, 8) CTAs of that kernel the current device holds at once; 0: none.
+int64_t coop_cluster_capacity(int cluster);
 
 // K5: x[:, a_ch:, :, :] += sign * Round_nbits(t)            couplelib.py:49-51,58-59; roundlib.py:18-38
 //   x: (batch, channels, hw) contiguous;  t: (batch, channels - a_ch, hw) contiguous

@@ -266,15 +266,19 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         const uint32_t hi0 = hi;                     // state < 2^32 iff the high word is zero
         hi = hi0 == 0u ? lo : hi0;
         lo = hi0 == 0u ? next_word : lo;
-        wrem -= hi0 == 0u ? 1 : 0;
-        // if (hi0 == 0 && wrem > 0) next_word = wbase[wrem - 1], as a predicated load (the address
-        // is formed unconditionally: one multiply-add against selects and moves under a predicate)
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
-                     "setp.eq.u32 p, %1, 0;\n\t"
-                     "setp.gt.and.s32 p, %2, 0, p;\n\t"
-                     "mad.wide.s32 a, %2, 4, %3;\n\t"
-                     "@p ld.global.nc.u32 %0, [a+-4];\n\t}"
-                     : "+r"(next_word) : "r"(hi0), "r"(wrem), "l"(wbase));
+        // if (hi0 == 0) { --wrem; if (wrem > 0) next_word = wbase[wrem - 1]; }, predicated: no
+        // divergent branch (with 32 lanes, some lane renormalises at nearly every symbol); the
+        // address is formed unconditionally (two shift-adds against selects under a predicate; zero
+        // extension is as good as sign extension for an address that is only used when wrem > 0)
+        asm volatile("{\n\t.reg .pred p, q;\n\t.reg .u64 a;\n\t"
+                     "setp.eq.u32 p, %2, 0;\n\t"
+                     "@p add.s32 %1, %1, -1;\n\t"
+                     "setp.gt.and.s32 q, %1, 0, p;\n\t"
+                     "cvt.u64.u32 a, %1;\n\t"
+                     "shl.b64 a, a, 2;\n\t"
+                     "add.s64 a, a, %3;\n\t"
+                     "@q ld.global.nc.u32 %0, [a+-4];\n\t}"
+                     : "+r"(next_word), "+r"(wrem) : "r"(hi0), "l"(wbase));
     };
 
     if (n_iter > 0) stage(0);
@@ -336,24 +340,33 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     }
 }
 
-// Stream count up to which the CTA-per-stream kernel (rans_decode_coop.cu) is used: two CTAs of
-// it fit an SM, and within that one wave every stream decodes 1.3x (rans/test.py's mixture of
-// distributions) to 3x (narrow distributions) faster than a lane of the lane-per-stream kernel;
-// a second wave would cost more than it gains (measured crossover: 296 -> 444 streams).
-// FLIC_DEC_COOP_MAX_STREAMS overrides the count (0 disables); flic_set_decode_kernel() forces
-// either kernel.
+// Kernel choice by stream count.
+//   * up to the number of 8-, 4-, 2-CTA clusters the device holds at once: a cluster per stream
+//     (rans_decode_coop.cu, K3d) -- the whole wave of streams runs concurrently and every stream has
+//     16 to 112 producer warps on other SMs tabulating for it;
+//   * up to two CTAs per SM: a CTA per stream (K3c); within that one wave every stream decodes 1.3x
+//     (rans/test.py's mixture of distributions) to 3x (narrow distributions) faster than a lane of the
+//     lane-per-stream kernel; a second wave would cost more than it gains (measured crossover:
+//     296 -> 444 streams);
+//   * more: a lane per stream.
+// FLIC_DEC_COOP_MAX_STREAMS overrides the CTA-per-stream count (0 disables both cooperative
+// kernels); flic_set_decode_kernel() forces a kernel.
 static std::atomic<int> g_decode_kernel{-1};
 int set_decode_kernel(int which) { return g_decode_kernel.exchange(which); }
 
-static int64_t coop_decode_max_streams() {
+// 0: lane per stream; 1: CTA per stream; 2, 4, 8: cluster per stream
+static int decode_kernel_for(int64_t n_streams) {
     const int forced = g_decode_kernel.load(std::memory_order_relaxed);
-    if (forced == 0) return 0;
-    if (forced == 1) return INT64_MAX;
+    if (forced == 0 || forced == 1) return forced;
+    if (forced == 2 || forced == 4 || forced == 8) return coop_cluster_capacity(forced) > 0 ? forced : 1;
     static const int64_t env = [] {
         const char* e = getenv("FLIC_DEC_COOP_MAX_STREAMS");
         return e ? (int64_t)atoll(e) : (int64_t)-1;
     }();
-    return env >= 0 ? env : 2 * (int64_t)sm_count();
+    if (env == 0) return 0;
+    for (int c = 8; c >= 2; c >>= 1)
+        if (n_streams <= coop_cluster_capacity(c)) return c;
+    return n_streams <= (env >= 0 ? env : 2 * (int64_t)sm_count()) ? 1 : 0;
 }
 
 cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offsets,
@@ -362,10 +375,11 @@ cudaError_t launch_rans_decode(const uint32_t* packed, const int64_t* word_offse
                                uint64_t* end_states, int32_t* status, int check_end,
                                WordsLeft left, cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
-    if (n_streams <= coop_decode_max_streams()) {
-        note_coder_kernel(1, "rans_decode_coop_kernel");
+    if (const int k = decode_kernel_for(n_streams)) {
+        note_coder_kernel(1, k == 1 ? "rans_decode_coop_kernel" : k == 2 ? "rans_decode_coop_kernel<cluster 2>"
+                                     : k == 4 ? "rans_decode_coop_kernel<cluster 4>" : "rans_decode_coop_kernel<cluster 8>");
         return launch_rans_decode_coop(packed, word_offsets, states, mean, scale, offsets, n_streams, x_out,
-                                       end_states, status, check_end, left, stream);
+                                       end_states, status, check_end, left, k, stream);
     }
     const int64_t warps = (n_streams + kLanes - 1) / kLanes;
     const bool small = warps <= (int64_t)sm_count() * 16;

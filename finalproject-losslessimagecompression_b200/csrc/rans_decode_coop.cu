@@ -25,22 +25,77 @@
 // in the lane kernel, by all lanes at once.  Groups are double-buffered with one CTA barrier per
 // group.  Results are bit-identical by construction: the window holds exact CDF values and the
 // search returns the smallest in-window s with CDF(s) > mod (CDF is non-decreasing).
+//
+// K3d -- the same with a thread-block CLUSTER per stream (a handful of streams: the reference's
+// own partition is one stream per latent level, trainer.py:308-318, and one stream in
+// rans/test.py).  With one CTA the producers keep up only with narrow distributions, so symbols
+// wider than 12 bins per scale unit (a quarter of rans/test.py's mixture) are decoded on the chain
+// at ~1000 cycles each.  A cluster of 2, 4 or 8 CTAs puts 16 producer warps on each of the other
+// SMs of the cluster; they write their chunks straight into the home CTA's shared memory
+// (st.shared::cluster through a mapa-translated address, distributed shared memory), groups are
+// handed over with the cluster barrier, and the window grows to 32 chunks (1024 bins, 5.1 scale
+// units either side up to a scale of 100 bins), which the chain searches in two ballots (chunk
+// index, then entry).  The home CTA keeps the chain's scheduler free: its own producers, if any,
+// are the warps of the other three sub-partitions.
 #include "flic_device.cuh"
 #include "flic_kernels.cuh"
 
+#include <type_traits>
+
 namespace flic {
 
-constexpr int kCoopProducers = 7;     // producer warps per CTA; warp kCoopProducers is the consumer (more
-                                      // producers take issue slots from the chain: 15 cost it 17 %)
-constexpr int kCoopSlots = 160;       // 32-entry slots per group buffer (40 KB; two buffers)
 #ifndef FLIC_COOP_UNROLL
 #define FLIC_COOP_UNROLL 4
 #endif
+#ifndef FLIC_CLUSTER_HOME_PRODUCERS
+#define FLIC_CLUSTER_HOME_PRODUCERS 1
+#endif
 constexpr int kCoopUnroll = FLIC_COOP_UNROLL;   // evaluations a producer warp interleaves
-constexpr int kCoopMaxChunks = 8;     // 32-bin chunks per symbol window (at most 256 bins)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCoopSlotBase = 2560;     // bytes of shared memory in front of the slots
 constexpr int kNever = 0x7fffffff;    // p = v = kNever: an empty interval no mod falls into
+
+// Geometry by cluster size C (CTAs per stream).
+template <int C>
+struct CoopCfg {
+    // C == 1: warps 0..6 produce, warp 7 is the consumer (more producers take issue slots from the
+    // chain: 15 cost it 17 %); two CTAs fit an SM.  C > 1: 16 warps per CTA, the last one of the home
+    // CTA is the consumer, alone on its sub-partition.
+    static constexpr int kWarps = C == 1 ? 8 : 16;
+    static constexpr int kConsumerWarp = kWarps - 1;
+    static constexpr int kHomeProducers = C == 1 ? 7 : (FLIC_CLUSTER_HOME_PRODUCERS ? 12 : 0);
+    static constexpr int kProducers = kHomeProducers + (C - 1) * kWarps;   // per stream
+    static constexpr int kSlots = C == 1 ? 160 : 448;     // 32-entry slots per group buffer (two buffers)
+    static constexpr int kMaxChunks = C == 1 ? 4 : 32;    // 32-bin chunks per symbol window
+    static constexpr size_t kSmemBytes = kCoopSlotBase + 8u * 2 * kSlots * 32;
+};
+
+// ---- cluster plumbing (C > 1) ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `local_shared_addr` in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local_shared_addr, uint32_t rank) {
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_shared_addr), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int C>
+__device__ __forceinline__ void group_sync() {
+    if constexpr (C == 1) cta_sync();
+    else cluster_sync_all();
+}
+// one tabulated value into entry `e` of the home CTA's slot memory (byte address `a` of the entry)
+template <int C>
+__device__ __forceinline__ void st_slot(uint32_t a, int v) {
+    if constexpr (C == 1) asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+    else asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 
 // One tabulated bin: v = CDF(bin), p = CDF(bin - 1).  The symbol is the one entry with
 // p <= mod < v, a test each lane makes on its own; (p, v - p) are the (start, freq) of the pop.
@@ -73,15 +128,20 @@ struct CoopGroup {
     int total;       // tasks of the group
 };
 
-// Every warp of the CTA computes the same description from the same inputs, so no metadata has
-// to cross warps.
+// Every warp of the CTA (of the cluster) computes the same description from the same inputs, so no
+// metadata has to cross warps.
 //
 // Window: one chunk (15 bins either side of the mode) up to a logistic scale of 3 bins (1.3 % of
 // a logistic's mass lies outside, and a symbol there costs a few hundred cycles on the chain);
-// up to 12 bins, 5.1 scale units either side in 2 to 4 chunks, which the chain searches in two
-// steps; wider distributions are not tabulated: at ~45 cycles per chunk (7 producer warps) the
-// tabulation would take as long as the lane kernel's step, which is what those symbols get.
+// above that 5.1 scale units either side, in 2 to kMaxChunks chunks, which the chain searches in
+// two steps.  One CTA: up to 12 bins per scale unit (4 chunks); wider distributions are not
+// tabulated there: at ~45 cycles per chunk (7 producer warps) the tabulation would take as long as
+// the lane kernel's step, which is what those symbols get.  A cluster tabulates every width (32
+// chunks cover 5.1 scale units up to a scale of 100 bins, and 3.4 at the 148 bins that end
+// rans/test.py's range).
+template <int C>
 __device__ __forceinline__ CoopGroup coop_describe(float mean, float scale, bool valid, int lane, CoopSymbol& d) {
+    using Cfg = CoopCfg<C>;
     d.mean = mean;
     d.scale = scale;
     d.m = make_model(mean, scale);
@@ -89,7 +149,10 @@ __device__ __forceinline__ CoopGroup coop_describe(float mean, float scale, bool
     const bool ok = valid && params_ok(mean, scale);
     int n = 0;
     if (ok && cb <= 3.0f) n = 1;
-    else if (ok && cb <= 12.0f) n = (2 * ((int)(cb * 5.1f) + 2) + 31) >> 5;  // <= (2 * 63 + 31) / 32 = 4
+    else if (ok && (C > 1 || cb <= 12.0f)) {
+        n = (2 * ((int)(fminf(cb, 128.0f) * 5.1f) + 2) + 31) >> 5;  // C == 1: <= (2 * 63 + 31) / 32 = 4
+        n = n < Cfg::kMaxChunks ? n : Cfg::kMaxChunks;
+    }
     const int many = n > 1 ? n : 0;
     int incl = many;
 #pragma unroll
@@ -97,39 +160,44 @@ __device__ __forceinline__ CoopGroup coop_describe(float mean, float scale, bool
         const int o = __shfl_up_sync(kFull, incl, s);
         if (lane >= s) incl += o;
     }
-    if (32 + incl > kCoopSlots) n = 0;              // over capacity: decoded on the chain
+    if (many && 32 + incl > Cfg::kSlots) n = 0;     // over capacity: decoded on the chain
     d.t_off = 32 + incl - many;
     d.n = ok ? n : -1;
-    // centred on the mode (lower + 1024 = round(256 mean)): with at most 256 bins either side the
+    // centred on the mode (lower + 1024 = round(256 mean)): with at most 512 bins either side the
     // window lies strictly inside the coder's 2048-bin support, so it needs no edge cases
     d.w0 = d.m.lower + 1024 - 16 * n + 1;
     CoopGroup grp;
     grp.ones = __ballot_sync(kFull, n == 1);
     grp.multis = __ballot_sync(kFull, n > 1);
     grp.n_ones = __popc(grp.ones);
-    grp.total = grp.n_ones + __shfl_sync(kFull, incl, 31);
+    // tasks of symbols that went over capacity are not evaluated: the count stops at the last slot in use
+    const int used = __reduce_max_sync(kFull, n > 1 ? incl : 0);
+    grp.total = grp.n_ones + used;
     return grp;
 }
 
-__global__ void __launch_bounds__((kCoopProducers + 1) * 32)
+template <int C>
+__global__ void __launch_bounds__(CoopCfg<C>::kWarps * 32)
 rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ word_offsets,
                         const uint64_t* __restrict__ states, const float* __restrict__ mean,
                         const float* __restrict__ scale, const int64_t* __restrict__ offsets,
                         int64_t n_streams, float* __restrict__ x_out, uint64_t* __restrict__ end_states,
                         int32_t* __restrict__ status, int check_end, WordsLeft left) {
+    using Cfg = CoopCfg<C>;
+    constexpr int kSlots = Cfg::kSlots;
     extern __shared__ __align__(256) unsigned char s_raw[];
     uint64_t* const s_tab = reinterpret_cast<uint64_t*>(s_raw);                              // 256 B
     int* const s_code = reinterpret_cast<int*>(s_raw + 512);                                 // 32 x 4 B (consumer only)
     unsigned* const s_who = reinterpret_cast<unsigned*>(s_raw + 640);                        // 32 x 4 B (consumer only)
     int* const s_toff = reinterpret_cast<int*>(s_raw + 768);                                 // 32 x 4 B (consumer only)
     int4* const s_par = reinterpret_cast<int4*>(s_raw + 1024);                               // 32 x 48 B (consumer only)
-    CoopEntry (*const s_slot)[kCoopSlots][32] =
-        reinterpret_cast<CoopEntry (*)[kCoopSlots][32]>(s_raw + kCoopSlotBase);              // [2][slots][32]
+    // slots: [2][kSlots][32] CoopEntry from s_raw + kCoopSlotBase, in the HOME CTA (cluster rank 0)
     const ExpTab tab = stage_exp_table(s_tab);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int64_t stream = blockIdx.x;
+    const uint32_t rank = C == 1 ? 0u : cluster_ctarank();
+    const int64_t stream = C == 1 ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x / C);
     const int64_t beg = offsets[stream];
     int64_t len = offsets[stream + 1] - beg;
     const int64_t wbeg = word_offsets[stream];
@@ -140,6 +208,8 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     const int n_groups = (int)((len + 31) >> 5);
     const float* const mean_s = mean + beg;
     const float* const scale_s = scale + beg;
+    // every CTA of the cluster is running before anybody writes into the home CTA's shared memory
+    if constexpr (C > 1) cluster_sync_all();
 
     // group g holds the symbols [len - 32 (g + 1), len - 32 g) that exist; lane j <-> the j-th of them
     auto load_group = [&](int g, float& mu, float& sc) -> bool {
@@ -150,24 +220,39 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         return valid;
     };
 
-    if (warp < kCoopProducers) {
+    // roles.  One CTA: warps 0..6 produce.  Cluster: in the home CTA the warps of sub-partitions
+    // 0..2 (warp & 3 != 3; the consumer is alone on sub-partition 3), in the others all 16.
+    const bool is_consumer = rank == 0 && warp == Cfg::kConsumerWarp;
+    int producer = -1;                                  // index among the stream's producer warps
+    if constexpr (C == 1) {
+        producer = warp < Cfg::kHomeProducers ? warp : -1;
+    } else {
+        if (rank != 0) producer = Cfg::kHomeProducers + ((int)rank - 1) * Cfg::kWarps + warp;
+        else if (Cfg::kHomeProducers && (warp & 3) != 3) producer = (warp >> 2) * 3 + (warp & 3);
+    }
+
+    if (producer >= 0) {
         // ------------------------------------------------------------------ producers
+        uint32_t slot_base = (uint32_t)__cvta_generic_to_shared(s_raw) + (uint32_t)kCoopSlotBase;
+        if constexpr (C > 1) slot_base = cluster_map(slot_base, 0u);
         float mu, sc;
         bool valid = load_group(0, mu, sc);
         for (int g = 0; g < n_groups; ++g) {
             CoopSymbol d;
-            const CoopGroup grp = coop_describe(mu, sc, valid, lane, d);
+            const CoopGroup grp = coop_describe<C>(mu, sc, valid, lane, d);
             valid = load_group(g + 1, mu, sc);          // in flight during the evaluations
-            CoopEntry (*const slot)[32] = s_slot[g & 1];
-            // kCoopUnroll tasks per pass: their evaluations are independent and interleave (a lone
-            // warp is latency-bound on the ~35-deep dependency chain of one evaluation)
-            for (int t0 = warp; t0 < grp.total; t0 += kCoopUnroll * kCoopProducers) {
-                int bins[kCoopUnroll], cs[kCoopUnroll], ns[kCoopUnroll], js[kCoopUnroll], slots[kCoopUnroll];
-                bool on[kCoopUnroll];
-                SymbolModel mj[kCoopUnroll];
+            const uint32_t buf = slot_base + (uint32_t)(g & 1) * (uint32_t)(kSlots * 256);
+            // U tasks per pass: their evaluations are independent and interleave (a lone warp is
+            // latency-bound on the ~35-deep dependency chain of one evaluation); a warp whose share
+            // of the group is a single task evaluates just that one
+            auto run_tasks = [&](auto uc, int t0) {
+                constexpr int U = decltype(uc)::value;
+                int bins[U], cs[U], ns[U], js[U], slots[U];
+                bool on[U];
+                SymbolModel mj[U];
 #pragma unroll
-                for (int u = 0; u < kCoopUnroll; ++u) {
-                    const int t = t0 + u * kCoopProducers;
+                for (int u = 0; u < U; ++u) {
+                    const int t = t0 + u * Cfg::kProducers;
                     int j, c, sl;
                     if (t < grp.n_ones) {               // the t-th single-chunk symbol, in its head slot
                         j = (int)__fns(grp.ones, 0, t + 1);
@@ -188,39 +273,46 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                     mj[u].lower = __shfl_sync(kFull, d.m.lower, j);
                     bins[u] = __shfl_sync(kFull, d.w0, j) - 1 + 32 * c + lane;
                 }
-                int v[kCoopUnroll];
+                int v[U];
 #pragma unroll
-                for (int u = 0; u < kCoopUnroll; ++u) v[u] = cdf_at(bins[u], mj[u], tab);
+                for (int u = 0; u < U; ++u) v[u] = cdf_at(bins[u], mj[u], tab);
 #pragma unroll
-                for (int u = 0; u < kCoopUnroll; ++u) {
+                for (int u = 0; u < U; ++u) {
                     if (!on[u]) continue;
                     const int c = cs[u], n = ns[u];
-                    CoopEntry* const row = slot[slots[u]];
+                    // entry e of slot sl: byte address buf + 256 sl + 8 e; .p at +0, .v at +4
+                    const uint32_t row = buf + 256u * (uint32_t)slots[u] + 8u * (uint32_t)lane;
                     // v is this entry's value and the next entry's p; the window's very first entry
                     // has no left neighbour and can never be the symbol (empty interval p == v; the
                     // chain tests (mod - p) < (v - p) in unsigned arithmetic)
-                    row[lane].v = v[u];
-                    if (lane < 31) row[lane + 1].p = v[u];
-                    else if (c + 1 < n) row[32].p = v[u];          // entry 0 of the next chunk
-                    if (lane == 0 && c == 0) row[0].p = v[u];       // p == v: an empty interval
+                    st_slot<C>(row + 4u, v[u]);
+                    if (lane < 31 || c + 1 < n) st_slot<C>(row + 8u, v[u]);   // lane 31: entry 0 of the next chunk
+                    if (lane == 0 && c == 0) st_slot<C>(row, v[u]);            // p == v: an empty interval
                     if (n > 1) {
                         // index (head slot): entry c = (last value of chunk c - 1, last value of chunk c), so that
                         // p <= mod < v picks the chunk that holds the symbol; entries >= n never match
-                        CoopEntry* const index = slot[js[u]];
+                        const uint32_t index = buf + 256u * (uint32_t)js[u];
                         if (lane == 31) {
-                            index[c].v = v[u];
-                            if (c + 1 < n) index[c + 1].p = v[u];
+                            st_slot<C>(index + 8u * (uint32_t)c + 4u, v[u]);
+                            if (c + 1 < n) st_slot<C>(index + 8u * (uint32_t)(c + 1), v[u]);
                         }
                         if (c == 0) {
-                            if (lane == 0) index[0].p = -1;
-                            if (lane >= n) { index[lane].p = kNever; index[lane].v = kNever; }
+                            if (lane == 0) st_slot<C>(index, -1);
+                            if (lane >= n) { st_slot<C>(index + 8u * (uint32_t)lane, kNever); st_slot<C>(index + 8u * (uint32_t)lane + 4u, kNever); }
                         }
                     }
                 }
+            };
+            for (int t0 = producer; t0 < grp.total; t0 += kCoopUnroll * Cfg::kProducers) {
+                if (t0 + Cfg::kProducers >= grp.total) run_tasks(std::integral_constant<int, 1>{}, t0);
+                else run_tasks(std::integral_constant<int, kCoopUnroll>{}, t0);
             }
-            cta_sync();   // group g tabulated; the consumer has finished group g - 1
+            group_sync<C>();   // group g tabulated; the consumer has finished group g - 1
         }
-        cta_sync();       // pairs with the consumer's barrier after the last group
+        group_sync<C>();       // pairs with the consumer's barrier after the last group
+    } else if (!is_consumer) {
+        // ------------------------------------------------------------------ idle warps of the home CTA
+        for (int g = 0; g <= n_groups; ++g) group_sync<C>();
     } else {
         // ------------------------------------------------------------------ consumer
         const uint32_t* const wbase = packed + wbeg;
@@ -285,7 +377,7 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         bool valid = load_group(0, mu, sc);
         for (int g = 0; g < n_groups; ++g) {
             CoopSymbol d;
-            const CoopGroup grp = coop_describe(mu, sc, valid, lane, d);
+            const CoopGroup grp = coop_describe<C>(mu, sc, valid, lane, d);
             const int64_t base = len - 32 * (int64_t)(g + 1);
             const int j_lo = base < 0 ? (int)(-base) : 0;   // first group-slot that is a symbol
             valid = load_group(g + 1, mu, sc);
@@ -297,15 +389,14 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
             s_code[lane] = 0;
             s_toff[lane] = d.t_off;
             __syncwarp();
-            cta_sync();   // group g tabulated
-            const CoopEntry (*const slot)[32] = s_slot[g & 1];
+            group_sync<C>();   // group g tabulated
             // A warp issues in order: whatever sits in front of an instruction in the stream delays
             // it, needed or not.  So the common case -- a single-chunk symbol found in its window --
             // gets a loop of its own with nothing else in it: the head entry is read one symbol ahead
             // (fixed address: slot j), "single-chunk" is a bit of `ones`, the decoded value is worked
             // out after the loop from the ballot each step leaves behind, and anything else LEAVES
             // the loop, is decoded out of line, and the loop is entered again.
-            const uint32_t sm_slot = sm + (uint32_t)kCoopSlotBase + (uint32_t)(g & 1) * (uint32_t)(kCoopSlots * 256) + 8u * (uint32_t)lane;
+            const uint32_t sm_slot = sm + (uint32_t)kCoopSlotBase + (uint32_t)(g & 1) * (uint32_t)(kSlots * 256) + 8u * (uint32_t)lane;
             // One single-chunk symbol: this lane's candidate for the popped state and whether the
             // lane's entry is the symbol's.  (h, l) is the state after the word pull.
             struct Cand { uint32_t hi, lo; bool mine; };
@@ -345,7 +436,7 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                 const uint32_t hi0 = hi, h = hi0 == 0u ? lo : hi0, l = hi0 == 0u ? w_next : lo;   // pulled state
                 const int mod = (int)(l & kProbMask);
                 const unsigned which = __ballot_sync(kFull, index.p <= mod && mod < index.v);
-                const int c = __popc(which - 1u) & (kCoopMaxChunks - 1);       // one bit set: its index
+                const int c = __popc(which - 1u) & 31;       // one bit set: its index
                 const Cand cd = candidate(lds_entry(sm_slot + 256u * (uint32_t)(t_off + c)), h, l);
                 const unsigned who = __ballot_sync(kFull, cd.mine);
                 const uint32_t rhi = __reduce_or_sync(kFull, cd.mine ? cd.hi : 0u);
@@ -453,7 +544,7 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                 x_s[base + lane] = (float)(d.w0 - 1 + s_code[lane] + __ffs((int)s_who[lane]) - 1) * 0.00390625f;   // s / 256., exact
             __syncwarp();
         }
-        cta_sync();
+        group_sync<C>();
         if (lane == 0) {
             flags |= guard_flags(guard);
             if (wrem < 0) flags |= ST_UNDERRUN;
@@ -466,20 +557,84 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     }
 }
 
-constexpr size_t kCoopSmemBytes = kCoopSlotBase + sizeof(CoopEntry) * 2 * kCoopSlots * 32;
+template <int C>
+static cudaError_t launch_coop(const uint32_t* packed, const int64_t* word_offsets, const uint64_t* states,
+                               const float* mean, const float* scale, const int64_t* offsets, int64_t n_streams,
+                               float* x_out, uint64_t* end_states, int32_t* status, int check_end, WordsLeft left,
+                               cudaStream_t stream) {
+    using Cfg = CoopCfg<C>;
+    cudaError_t e = cudaFuncSetAttribute(rans_decode_coop_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_streams * C));
+    cfg.blockDim = dim3(Cfg::kWarps * 32);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = C > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, rans_decode_coop_kernel<C>, packed, word_offsets, states, mean, scale, offsets,
+                              n_streams, x_out, end_states, status, check_end, left);
+}
 
+// Clusters of `cluster` CTAs that can be resident at once on the current device (0: not supported),
+// cached per device and cluster size.
+int64_t coop_cluster_capacity(int cluster) {
+    constexpr int kMaxDevices = 64;
+    static std::atomic<int> cache[kMaxDevices][4] = {};
+    const int slot = cluster == 2 ? 1 : cluster == 4 ? 2 : cluster == 8 ? 3 : 0;
+    if (slot == 0) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    int n = cache[dev][slot].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3(cluster);
+        cudaError_t e = cudaSuccess;
+        int k = 0;
+        auto query = [&](auto kernel, size_t smem, int threads) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = smem;
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&k, kernel, &cfg);
+        };
+        if (cluster == 2) query(rans_decode_coop_kernel<2>, CoopCfg<2>::kSmemBytes, CoopCfg<2>::kWarps * 32);
+        else if (cluster == 4) query(rans_decode_coop_kernel<4>, CoopCfg<4>::kSmemBytes, CoopCfg<4>::kWarps * 32);
+        else query(rans_decode_coop_kernel<8>, CoopCfg<8>::kSmemBytes, CoopCfg<8>::kWarps * 32);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); k = 0; }
+        n = k > 0 ? k : -1;
+        cache[dev][slot].store(n, std::memory_order_relaxed);
+    }
+    return n > 0 ? n : 0;
+}
+
+// cluster: CTAs per stream (1, 2, 4 or 8)
 cudaError_t launch_rans_decode_coop(const uint32_t* packed, const int64_t* word_offsets,
                                     const uint64_t* states, const float* mean, const float* scale,
                                     const int64_t* offsets, int64_t n_streams, float* x_out,
                                     uint64_t* end_states, int32_t* status, int check_end,
-                                    WordsLeft left, cudaStream_t stream) {
+                                    WordsLeft left, int cluster, cudaStream_t stream) {
     if (n_streams <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(rans_decode_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kCoopSmemBytes);
-    if (e != cudaSuccess) return e;
-    rans_decode_coop_kernel<<<(unsigned)n_streams, (kCoopProducers + 1) * 32, kCoopSmemBytes, stream>>>(
-        packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, left);
-    return cudaGetLastError();
+#define FLIC_COOP_ARGS packed, word_offsets, states, mean, scale, offsets, n_streams, x_out, end_states, status, check_end, left, stream
+    switch (cluster) {
+        case 8: return launch_coop<8>(FLIC_COOP_ARGS);
+        case 4: return launch_coop<4>(FLIC_COOP_ARGS);
+        case 2: return launch_coop<2>(FLIC_COOP_ARGS);
+        default: return launch_coop<1>(FLIC_COOP_ARGS);
+    }
+#undef FLIC_COOP_ARGS
 }
 
 }  // namespace flic

@@ -20,7 +20,9 @@
 // stream counts where a lane-per-stream kernel would leave them idle, and a single long stream
 // still gets 8 warps' worth of table evaluation.
 // The (start, freq) tables never touch HBM: algorithmic traffic is the 12 B/symbol of inputs plus
-// the coded bits.  Tile pitch is 33 uint2 so the consumer's lane-per-row reads are conflict free.
+// the coded bits.  Tile pitch is 33 entries so the consumer's lane-per-row reads spread over the banks;
+// an entry carries the reciprocal the push needs, computed by the producers (it does not depend on
+// the state), so the consumer's chain is convert -> multiply -> fix-up.
 #include "flic_device.cuh"
 #include "flic_kernels.cuh"
 
@@ -56,7 +58,8 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                    uint32_t* __restrict__ scratch, int64_t* __restrict__ counts,
                    uint64_t* __restrict__ states, int32_t* __restrict__ status) {
     __shared__ __align__(256) uint64_t s_tab[32];
-    __shared__ uint2 s_tile[2][kLanes][kTile + 1];
+    // (start, freq) and the biased reciprocal of freq the push divides with (flic_core.cuh: rans_push_rf)
+    __shared__ uint4 s_tile[2][kLanes][kTile + 1];
     __shared__ int64_t s_beg[kLanes], s_len[kLanes];
     __shared__ int32_t s_flags[kLanes];
     __shared__ int64_t s_max_len;
@@ -83,7 +86,7 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
         // ------------------------------------------------------------------ producers
         const int pw = warp - 1;
         for (int64_t k = 0; k < n_tiles; ++k) {
-            uint2(*tile)[kTile + 1] = s_tile[k & 1];
+            uint4(*tile)[kTile + 1] = s_tile[k & 1];
             const int64_t i = k * kTile + lane;
 #pragma unroll 1
             for (int r0 = pw * kRowBatch; r0 < kLanes; r0 += PRODUCERS * kRowBatch) {
@@ -108,7 +111,8 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                     if (on[q]) {
                         int32_t f = 0;
                         const SymbolTable e = make_table(xv[q], mv[q], sv[q], tab, f);
-                        tile[r][lane] = make_uint2(e.start, e.freq);
+                        const double rf = push_reciprocal(e.freq);
+                        tile[r][lane] = make_uint4(e.start, e.freq, (uint32_t)__double2loint(rf), (uint32_t)__double2hiint(rf));
                         if (f) atomicOr(&s_flags[r], f);  // rare
                     }
                 }
@@ -125,15 +129,15 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
         int64_t wpos = beg;  // the stream's scratch region starts at its first symbol index
         cta_sync();          // tile 0 complete
         for (int64_t k = 0; k < n_tiles; ++k) {
-            uint2(*tile)[kTile + 1] = s_tile[k & 1];
+            uint4(*tile)[kTile + 1] = s_tile[k & 1];
             const int64_t rem = len - k * kTile;
             const int cnt = rem >= kTile ? kTile : (rem > 0 ? (int)rem : 0);
 #pragma unroll 4
             for (int j = 0; j < kTile; ++j) {
                 if (j < cnt) {
-                    const uint2 e = tile[lane][j];
+                    const uint4 e = tile[lane][j];
                     uint32_t word;
-                    if (rans_push(state, e.x, e.y, word)) scratch[wpos++] = word;
+                    if (rans_push_rf(state, e.x, e.y, __hiloint2double((int)e.w, (int)e.z), word)) scratch[wpos++] = word;
                 }
             }
             cta_sync();  // tile k consumed; tile k+1 complete

@@ -59,11 +59,18 @@ int64_t flic_kernel_launches(void);
 /* Name of the kernel the most recent flic_rans_encode (which = 0) / flic_rans_decode (which = 1)
  * launched: the coder has a lane-per-stream and a warp-cooperative variant of each (profiling aid). */
 const char* flic_last_coder_kernel(int which);
-/* Which decode kernel flic_rans_decode launches: -1 = by stream count (default: the CTA-per-stream
- * kernel up to two streams per SM, the lane-per-stream kernel above), 0 = always lane-per-stream,
- * 1 = always CTA-per-stream.  Process-wide; for measurements and for tests that compare the two
- * (their results are bit-identical by construction).  Returns the previous setting. */
+/* Which decode kernel flic_rans_decode launches: -1 = by stream count (default: a thread-block
+ * cluster of 8 / 4 / 2 CTAs per stream while all streams' clusters are resident at once -- the
+ * reference's own partitions of one to a few streams, trainer.py:308-318, rans/test.py:6-22 --,
+ * the CTA-per-stream kernel up to two streams per SM, the lane-per-stream kernel above),
+ * 0 = always lane-per-stream, 1 = always CTA-per-stream, 2 / 4 / 8 = always a cluster of that many
+ * CTAs per stream.  Process-wide; for measurements and for tests that compare them (their results
+ * are bit-identical by construction).  Returns the previous setting. */
 int flic_set_decode_kernel(int which);
+/* Streams the cluster-per-stream decode kernel can hold at once on the current device with clusters of
+ * `cluster` (2, 4 or 8) CTAs; 0 if the device cannot launch them.  The default choice uses the largest
+ * cluster size whose capacity covers the call's stream count. */
+int64_t flic_decode_cluster_capacity(int cluster);
 
 /* ------------------------------------------------------------------------------------------
  * Device entry points

@@ -305,7 +305,8 @@ def test_reciprocal_divisions_are_exact_on_the_device():
 # ---- the CTA-per-stream decoder (few streams) ----------------------------------------------------
 
 def _with_decode_kernel(which):
-    """Context manager: force the lane-per-stream (0) or the CTA-per-stream (1) decode kernel."""
+    """Context manager: force the lane-per-stream (0), the CTA-per-stream (1) or a cluster-per-stream
+    (2, 4, 8 CTAs) decode kernel."""
     import contextlib
     from flic_b200 import _lib
 
@@ -354,6 +355,44 @@ def test_cta_per_stream_decoder_is_bit_exact(oracle, kind, n_streams):
         xr0, end0, status0 = rans.decode_streams(enc, md, sd, offd)
         assert _lib.lib().flic_last_coder_kernel(1).decode() != "rans_decode_coop_kernel"
     assert torch.equal(xr0, xr) and torch.equal(end0, end) and torch.equal(status0, status)
+    # a thread-block cluster per stream (the other CTAs tabulate into the home CTA's shared memory)
+    for cluster in (2, 4, 8):
+        with _with_decode_kernel(cluster):
+            xc, endc, statusc = rans.decode_streams(enc, md, sd, offd)
+            assert _lib.lib().flic_last_coder_kernel(1).decode() == f"rans_decode_coop_kernel<cluster {cluster}>"
+        assert torch.equal(xc, xr) and torch.equal(endc, end) and torch.equal(statusc, status), cluster
+
+
+def test_cluster_per_stream_decoder_on_wide_and_mixed_windows(oracle):
+    """Every window class of the cluster decoder in one stream -- one chunk, an index of 2 to 32 chunks,
+    the 32-chunk cap (scales beyond 100 bins), symbols outside their window (up to 8 scale units from
+    the mode), a group that overflows the slot memory (32 wide symbols in a row) -- against the oracle's
+    bitstream, and the automatic choice for a handful of streams."""
+    from flic_b200 import rans, _lib
+    rng = np.random.default_rng(77)
+    n = 40_000
+    mean = rng.normal(0, 0.7, n).astype(np.float32)
+    logc = rng.uniform(-5, 5.2, n)
+    logc[10_000:10_640] = rng.uniform(4.0, 5.2, 640)          # twenty groups of wide symbols only
+    scale = (np.exp(logc) / 256).astype(np.float32)
+    u = rng.uniform(-8, 8, n)
+    x = np.round((mean.astype(np.float64) + scale.astype(np.float64) * u) * 256) / 256
+    lo = np.round(mean.astype(np.float64) * 256 - 1024)
+    x = (np.clip(x * 256, lo + 1, lo + 2046) / 256).astype(np.float32)
+    for n_streams in (1, 3, 5):
+        off = ragged_offsets(n, n_streams, 3 + n_streams)
+        words_o, woff_o, states_o, _ = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+        xd, md, sd = _cuda(x, mean, scale)
+        offd = torch.from_numpy(off).cuda()
+        enc = rans.encode_streams(xd, md, sd, offd)
+        assert np.array_equal(_u32(enc.words), words_o) and np.array_equal(_u64(enc.final_states), states_o)
+        xa, enda, sta = rans.decode_streams(enc, md, sd, offd)              # automatic choice
+        assert _lib.lib().flic_last_coder_kernel(1).decode().startswith("rans_decode_coop_kernel<cluster")
+        assert torch.equal(xa, xd) and not sta.any().item() and bool((enda == (1 << 32)).all().item())
+        for which in (0, 1, 2, 4, 8):
+            with _with_decode_kernel(which):
+                xr, end, st = rans.decode_streams(enc, md, sd, offd)
+            assert torch.equal(xr, xd) and torch.equal(end, enda) and torch.equal(st, sta), which
 
 
 def test_cta_per_stream_decoder_reports_what_the_lane_kernel_reports():
@@ -375,7 +414,7 @@ def test_cta_per_stream_decoder_reports_what_the_lane_kernel_reports():
     cut = rans.EncodedStreams(words, woff, enc.final_states, enc.status, enc.n_symbols)
     cut.word_offsets = woff.clone()
     res = []
-    for which in (0, 1):
+    for which in (0, 1, 2, 8):
         with _with_decode_kernel(which):
             # shorten stream 0 by pretending its words end three early (the words stay in place)
             wo = woff.clone()
@@ -383,7 +422,7 @@ def test_cta_per_stream_decoder_reports_what_the_lane_kernel_reports():
                                     torch.cat([wo[:1], wo[1:] - 3]), enc.final_states, enc.status, enc.n_symbols)
             xr, end, status = rans.decode_streams(e, bad_m, bad_s, off)
             res.append(status.cpu().tolist())
-    assert res[0] == res[1]
+    assert res[0] == res[1] == res[2] == res[3]
     st = res[1]
     assert st[0] & (_lib.ST_UNDERRUN | _lib.ST_BAD_END_STATE | _lib.ST_NO_SYMBOL)
     assert st[1] == 0                      # the empty stream
@@ -425,7 +464,7 @@ def test_chained_levels_equal_one_stream_over_the_concatenation(oracle, kind, n_
     assert np.array_equal(_u32(chained.words)[:nw], words_o)
     assert np.array_equal(_u64(chained.final_states), states_o)
     # decode with continuation, both kernels
-    for which in (0, 1):
+    for which in (0, 1, 4):
         with _with_decode_kernel(which):
             st, left = None, None
             for lvl in reversed(range(n_levels)):
@@ -460,3 +499,35 @@ def test_oracle_equals_the_reference_build_on_this_box(oracle, kind):
     xd, md, sd = _cuda(x, mean, scale)
     enc = rans.encode_streams(xd, md, sd)
     assert int(_u64(enc.final_states)[0]) == state_r and _u32(enc.words).tolist() == buf_r
+
+
+def test_tables_and_streams_on_window_origin_ties(oracle):
+    """The window origin is round(256 mean - 1024) with ties away from zero (rans.pyx:51,92); the kernels
+    compute it on the float pipe.  Means exactly on a tie, one float either side of it, on both sides of
+    mean = 4 (where 256 mean - 1024 changes sign): tables, bitstreams and the round trip against the oracle."""
+    from flic_b200 import rans
+    ks = np.arange(-1500, 1500, dtype=np.float64)
+    ties = ((ks + 0.5) / 256.0).astype(np.float32)
+    mean = np.concatenate([ties, np.nextafter(ties, np.float32(np.inf)), np.nextafter(ties, np.float32(-np.inf)),
+                           (ks / 256.0).astype(np.float32)]).astype(np.float32)
+    rng = np.random.default_rng(9)
+    mean = np.tile(mean, 4)
+    n = mean.size
+    scale = (np.exp(rng.uniform(-4, 2, n)) / 256).astype(np.float32)
+    lo = np.array([oracle.lib().flic_oracle_lower(__import__("ctypes").c_float(float(m))) for m in mean[: n // 4]])
+    lo = np.tile(lo, 4)
+    x = ((lo + rng.integers(900, 1150, n)) / 256.0).astype(np.float32)          # inside the window, near the mode
+    _, st_o, fr_o = oracle.tables(x, mean, scale)
+    xd, md, sd = _cuda(x, mean, scale)
+    start, freq, status = rans.cdf_tables(xd, md, sd)
+    assert int(status.item()) == 0
+    assert np.array_equal(_u32(start), st_o.astype(np.uint32)) and np.array_equal(_u32(freq), fr_o.astype(np.uint32))
+    off = ragged_offsets(n, 50, 4)
+    words_o, woff_o, states_o, _ = oracle.encode_streams(x, mean, scale, off, n_threads=8)
+    offd = torch.from_numpy(off).cuda()
+    enc = rans.encode_streams(xd, md, sd, offd)
+    assert np.array_equal(_u32(enc.words), words_o) and np.array_equal(_u64(enc.final_states), states_o)
+    for which in (0, 1, 4):
+        with _with_decode_kernel(which):
+            xr, end, st = rans.decode_streams(enc, md, sd, offd)
+            assert torch.equal(xr, xd) and not st.any().item() and bool((end == (1 << 32)).all().item())

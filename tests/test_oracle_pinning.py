@@ -225,3 +225,22 @@ def test_part1_from_float_argument_matches_reference_arithmetic(oracle, host_har
         nb, _ = oracle.part1_compare(b, np.array([g], np.int32))
         bad += nb
     assert bad == 0
+
+
+def test_window_origin_on_ties_and_edges(oracle, host_harness):
+    """lower = (int) round(mean * 256 - 1024) with C round (half away from zero), rans.pyx:51,92.  The
+    device header computes it on the float pipe (flic_core.cuh: lower_of); every tie (256 mean =
+    k + 0.5, both signs of mean * 256 - 1024), the floats next to each tie, tiny and large means."""
+    import ctypes as C
+    H = host_harness
+    ks = np.arange(-3000, 3000, dtype=np.float64)
+    ties = ((ks + 0.5) / 256.0).astype(np.float32)          # exact in float: (2k + 1) / 512
+    cand = [ties, np.nextafter(ties, np.float32(np.inf)), np.nextafter(ties, np.float32(-np.inf)),
+            (ks / 256.0).astype(np.float32), np.float32([0.0, -0.0, 1e-30, -1e-30, 4.0, 3.998046875, 4.001953125, 16384.0, -16384.0,
+                                                          16383.998, -16383.998, 1e-45, 1023.5 / 256, 1024.5 / 256])]
+    rng = np.random.default_rng(5)
+    cand.append(rng.normal(0, 2, 200_000).astype(np.float32))
+    cand.append((rng.uniform(-16384, 16384, 100_000)).astype(np.float32))
+    for arr in cand:
+        for mean in arr.tolist():
+            assert H.hh_lower(C.c_float(mean)) == oracle.lib().flic_oracle_lower(C.c_float(mean)), mean
