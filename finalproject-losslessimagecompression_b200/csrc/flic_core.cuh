@@ -516,10 +516,12 @@ FLIC_HD int part1_at(double a, const SymbolModel& m, ExpTab tab) {
 }
 
 // (double)xq + 1/512 = (2 s + 1) / 512 exactly, built without a conversion: the bits of
-// 1.5 * 2^43 + n / 512 are 0x42a8000000000000 + n (ulp 2^-9 in that binade).
+// 1.5 * 2^43 + (2^31 + n) / 512 are 0x42a80000:00000000 + 2^31 + n (ulp 2^-9 in that binade).  The
+// offset 2^31 keeps the low word from borrowing for negative n (|n| < 2^25), so the high word is a
+// constant and the low word one three-input add.
 FLIC_HD double half_bin_point(int s) {
-    const int n = 2 * s + 1;
-    return dsub(bits_f64(0x42a8000000000000ull + (uint64_t)(int64_t)n), 13194139533312.0);
+    const uint32_t lo = (uint32_t)s + (uint32_t)s + 0x80000001u;
+    return dsub(f64_from_words(0x42a80000u, lo), 13194143727616.0);   // 1.5 * 2^43 + 2^22
 }
 
 // CDF(s/256) for integer symbol s: part1 + part2, part2 = round((xq - lower_f) * 256) + 1
@@ -818,6 +820,10 @@ SymbolHit decode_symbol_search(uint32_t mod, float mean, float scale, ExpTab tab
     st.c_lo = -1; st.c_hi = -1; st.step = 2; st.done = false;
     if (!guess_in_window(g, m.lower)) {   // nothing is known yet: start from the nearest window end
         st.probe = clamp_to_window(g, m.lower);
+    } else if (g == m.lower && c_hi > (int)mod) {   // the window's left edge is virtual: "not greater"
+        SymbolHit h;
+        h.s = g; h.c_lo = c_lo; h.c_hi = c_hi;
+        return h;
     } else if (c_hi <= (int)mod) {  // answer is right of g
         st.lo = g; st.c_lo = c_hi;
         st.probe = g + 1 < st.hi ? g + 1 : st.hi;
@@ -844,8 +850,9 @@ FLIC_HD int decode_symbol_model(uint32_t& hi, uint32_t& lo, float mean, float sc
     int c_lo, c_hi;
     cdf_pair(g, m, tab, c_lo, c_hi);
     int s = g;
-    const bool left_ok = (g == m.lower) || (c_lo <= (int)mod);  // window's left edge is virtual
-    if (!(left_ok && c_hi > (int)mod && guess_in_window(g, m.lower))) {
+    // (a guess on the window's left edge whose CDF(g - 1) exceeds mod -- only a corrupt stream has
+    // that -- is sorted out by the search function: the edge is virtual)
+    if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower))) {
         const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
@@ -863,8 +870,9 @@ FLIC_HD int decode_symbol_lean(uint32_t& hi, uint32_t& lo, float mean, float sca
     int c_lo, c_hi;
     cdf_pair(g, m, tab, c_lo, c_hi);
     int s = g;
-    const bool left_ok = (g == m.lower) || (c_lo <= (int)mod);  // window's left edge is virtual
-    if (!(left_ok && c_hi > (int)mod && guess_in_window(g, m.lower))) {
+    // (a guess on the window's left edge whose CDF(g - 1) exceeds mod -- only a corrupt stream has
+    // that -- is sorted out by the search function: the edge is virtual)
+    if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower))) {
         const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
