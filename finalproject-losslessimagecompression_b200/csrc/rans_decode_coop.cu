@@ -10,21 +10,27 @@
 //
 // What does NOT depend on the state is the distribution: mean and scale of every symbol are
 // inputs.  So the exact CDF of symbol i can be tabulated before its turn comes, for the bins
-// where the symbol is likely to be: a window of 2 x (6 scale units + 3) bins around the mode
-// (99.5 % of a logistic's mass), at most 512 bins.  The CTA is split by role:
-//   producers (7 warps)  for the next group of 32 symbols: per-symbol model, window size and
-//       placement; then one exact CDF evaluation per lane per 32-bin chunk of every window
-//       (cdf_at(), the same function every other kernel uses), written to shared memory.
-//       Chunks of all 32 symbols form one task list that the warps share round-robin.
+// where the symbol is likely to be: a window of 5.1 scale units either side of the mode (98.8 % of
+// a logistic's mass).  The CTA is split by role:
+//   producers            for the next group of 32 symbols: per-symbol model, window size and
+//       placement; then one exact CDF evaluation per lane per 32-entry chunk of every window
+//       (cdf_at(), the same function every other kernel uses).  A chunk is built in registers --
+//       entry e = (CDF(b - 1), CDF(b)) of its bin b, the left value taken from the lane below --
+//       and stored with one 8-byte store per lane; consecutive chunks overlap by one bin, so no
+//       chunk needs a value another warp computes.  Chunks of all 32 symbols form one task list
+//       that the producer warps share round-robin.
 //   consumer (1 warp)    the chain.  All lanes hold the same state; per symbol: pull a word if
-//       needed, mod = state & 0xffffff, each lane compares one tabulated CDF value with mod,
-//       a ballot finds the first one above it, (start, end) are read back from the row and the
-//       state is popped -- about a hundred cycles instead of a thousand.
-// A symbol whose window was not tabulated (wide distribution, group over capacity, bad
-// parameters) or that falls outside it is decoded on the chain by decode_symbol_lean() exactly as
-// in the lane kernel, by all lanes at once.  Groups are double-buffered with one CTA barrier per
-// group.  Results are bit-identical by construction: the window holds exact CDF values and the
-// search returns the smallest in-window s with CDF(s) > mod (CDF is non-decreasing).
+//       needed, mod = state & 0xffffff, each lane tests its tabulated entry and computes the pop
+//       AS IF the entry were the symbol's, and an OR-reduction of the one lane that is right
+//       broadcasts the new state -- the chain is select, mask, subtract, multiply-add, select,
+//       reduce: under a hundred cycles instead of a thousand.  The stream's words wait in
+//       registers (64 at a time, one per lane, fetched by shuffle), so renormalisation puts no
+//       address arithmetic or load into the instruction stream of the chain.
+// A symbol whose window was not tabulated (group over capacity, bad parameters) or that falls
+// outside it is decoded on the chain by decode_symbol_model() exactly as in the lane kernel, by
+// all lanes at once.  Results are bit-identical by construction: the window holds exact CDF values
+// and the search returns the smallest in-window s with CDF(s) > mod (CDF is non-decreasing,
+// SURVEY A.2).
 //
 // K3d -- the same with a thread-block CLUSTER per stream (a handful of streams: the reference's
 // own partition is one stream per latent level, trainer.py:308-318, and one stream in
@@ -32,15 +38,26 @@
 // wider than 12 bins per scale unit (a quarter of rans/test.py's mixture) are decoded on the chain
 // at ~1000 cycles each.  A cluster of 2, 4 or 8 CTAs puts 16 producer warps on each of the other
 // SMs of the cluster; they write their chunks straight into the home CTA's shared memory
-// (st.shared::cluster through a mapa-translated address, distributed shared memory), groups are
-// handed over with the cluster barrier, and the window grows to 32 chunks (1024 bins, 5.1 scale
-// units either side up to a scale of 100 bins), which the chain searches in two ballots (chunk
-// index, then entry).  The home CTA keeps the chain's scheduler free: its own producers, if any,
-// are the warps of the other three sub-partitions.
+// (st.shared::cluster through a mapa-translated address: distributed shared memory), and the
+// window grows to 32 chunks (992 bins: 5.1 scale units either side up to a scale of 97 bins),
+// which the chain searches in two ballots (chunk index, then entry).  Groups cycle through three
+// buffers and are handed over with the cluster barrier split into its arrive and wait halves: the
+// consumer arrives for group g + 1 BEFORE it decodes group g and waits after, so the barrier's
+// latency (about a microsecond across SMs) is spent while the chain is busy.  The home CTA keeps
+// the chain's scheduler free: its own producers are the warps of the other three sub-partitions.
 #include "flic_device.cuh"
 #include "flic_kernels.cuh"
 
 #include <type_traits>
+#ifndef FLIC_COOP_STATS
+#define FLIC_COOP_STATS 0      // 1: the consumer counts the paths its symbols took and the cycles it waited (printf at the end)
+#endif
+#if FLIC_COOP_STATS
+#include <cstdio>
+#define COOP_STAT(...) __VA_ARGS__
+#else
+#define COOP_STAT(...)
+#endif
 
 namespace flic {
 
@@ -53,7 +70,8 @@ namespace flic {
 constexpr int kCoopUnroll = FLIC_COOP_UNROLL;   // evaluations a producer warp interleaves
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCoopSlotBase = 2560;     // bytes of shared memory in front of the slots
-constexpr int kNever = 0x7fffffff;    // p = v = kNever: an empty interval no mod falls into
+constexpr int kNever = 0x7fffffff;      // p = v = kNever: an empty interval no mod falls into
+constexpr int kChunkBins = 31;          // bins a chunk adds to its window (entry 0 only carries the left value)
 
 // Geometry by cluster size C (CTAs per stream).
 template <int C>
@@ -65,9 +83,11 @@ struct CoopCfg {
     static constexpr int kConsumerWarp = kWarps - 1;
     static constexpr int kHomeProducers = C == 1 ? 7 : (FLIC_CLUSTER_HOME_PRODUCERS ? 12 : 0);
     static constexpr int kProducers = kHomeProducers + (C - 1) * kWarps;   // per stream
-    static constexpr int kSlots = C == 1 ? 160 : 448;     // 32-entry slots per group buffer (two buffers)
-    static constexpr int kMaxChunks = C == 1 ? 4 : 32;    // 32-bin chunks per symbol window
-    static constexpr size_t kSmemBytes = kCoopSlotBase + 8u * 2 * kSlots * 32;
+    static constexpr int kBuffers = C == 1 ? 2 : 3;       // group buffers in flight
+    static constexpr int kSlots = C == 1 ? 160 : 296;     // 32-entry slots per group buffer
+    static constexpr int kMaxChunks = C == 1 ? 4 : 32;    // 32-bin chunks per wide window
+    static constexpr int kRows = (kSlots - 32) * 2;       // 128-byte rows (one chunk of a wide window each) behind the 32 head slots
+    static constexpr size_t kSmemBytes = kCoopSlotBase + 8u * kBuffers * kSlots * 32;
 };
 
 // ---- cluster plumbing (C > 1) ------------------------------------------------------------------
@@ -82,17 +102,20 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t local_shared_addr, uint
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_shared_addr), "r"(rank));
     return a;
 }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// The consumer's arrival only says "I have finished READING a buffer": nothing it wrote is for the
+// producers, so it needs no release fence (which would wait for its decoded-symbol stores to drain).
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+// one tabulated entry (8 bytes) into the home CTA's slot memory
 template <int C>
-__device__ __forceinline__ void group_sync() {
-    if constexpr (C == 1) cta_sync();
-    else cluster_sync_all();
+__device__ __forceinline__ void st_entry(uint32_t a, int p, int v) {
+    if constexpr (C == 1) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(p), "r"(v) : "memory");
+    else asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(p), "r"(v) : "memory");
 }
-// one tabulated value into entry `e` of the home CTA's slot memory (byte address `a` of the entry)
+
 template <int C>
-__device__ __forceinline__ void st_slot(uint32_t a, int v) {
+__device__ __forceinline__ void st_value(uint32_t a, int v) {
     if constexpr (C == 1) asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
     else asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
@@ -116,15 +139,14 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
 struct CoopSymbol {
     SymbolModel m;
     float mean, scale;
-    int n;       // chunks tabulated; 0: none (window around the guess, on the chain); -1: bad parameters
-                 // (scalar path, which flags them)
-    int t_off;   // n > 1: first chunk slot; entry e of chunk c stands for bin w0 - 1 + 32 c + e
-    int w0;
+    int n;       // chunks tabulated; 0: none (decoded on the chain); -1: bad parameters (on the chain, which flags them)
+    int t_off;   // n > 1: first row
+    int w0;      // window origin (see coop_describe)
 };
 struct CoopGroup {
     unsigned ones;   // symbols with n == 1
     unsigned multis; // symbols with n > 1
-    int n_ones;      // their number: tasks [0, n_ones) evaluate them, tasks from n_ones on the chunks >= 32
+    int n_ones;      // their number: tasks [0, n_ones) evaluate them, tasks from n_ones on the rows of the wide windows
     int total;       // tasks of the group
 };
 
@@ -137,21 +159,25 @@ struct CoopGroup {
 // two steps.  One CTA: up to 12 bins per scale unit (4 chunks); wider distributions are not
 // tabulated there: at ~45 cycles per chunk (7 producer warps) the tabulation would take as long as
 // the lane kernel's step, which is what those symbols get.  A cluster tabulates every width (32
-// chunks cover 5.1 scale units up to a scale of 100 bins, and 3.4 at the 148 bins that end
+// chunks cover 5.1 scale units up to a scale of 97 bins, and 3.3 at the 148 bins that end
 // rans/test.py's range).
-template <int C>
+// MODEL: also the FP64 model the evaluations need (producers); the consumer only needs the layout.
+template <int C, bool MODEL>
 __device__ __forceinline__ CoopGroup coop_describe(float mean, float scale, bool valid, int lane, CoopSymbol& d) {
     using Cfg = CoopCfg<C>;
     d.mean = mean;
     d.scale = scale;
-    d.m = make_model(mean, scale);
+    if constexpr (MODEL) d.m = make_model(mean, scale);
+    else d.m.lower = lower_of(mean);
     const float cb = scale * 256.0f;                // logistic scale in bins
     const bool ok = valid && params_ok(mean, scale);
     int n = 0;
     if (ok && cb <= 3.0f) n = 1;
     else if (ok && (C > 1 || cb <= 12.0f)) {
-        n = (2 * ((int)(fminf(cb, 128.0f) * 5.1f) + 2) + 31) >> 5;  // C == 1: <= (2 * 63 + 31) / 32 = 4
+        const int half = (int)(fminf(cb, 128.0f) * 5.1f) + 2;       // bins either side of the mode
+        n = (2 * half + 5 + 31) >> 5;                               // two more bins either side: the guess may be one off
         n = n < Cfg::kMaxChunks ? n : Cfg::kMaxChunks;
+        n = n < 2 ? 2 : n;
     }
     const int many = n > 1 ? n : 0;
     int incl = many;
@@ -160,12 +186,16 @@ __device__ __forceinline__ CoopGroup coop_describe(float mean, float scale, bool
         const int o = __shfl_up_sync(kFull, incl, s);
         if (lane >= s) incl += o;
     }
-    if (many && 32 + incl > Cfg::kSlots) n = 0;     // over capacity: decoded on the chain
-    d.t_off = 32 + incl - many;
+    if (many && incl > Cfg::kRows) n = 0;           // over capacity: decoded on the chain (narrowing every window
+                                                    // of the group in proportion instead was measured: worse on
+                                                    // rans/test.py's symbols, which lie uniformly within 5 scale units)
+    d.t_off = incl - many;                          // first row
     d.n = ok ? n : -1;
     // centred on the mode (lower + 1024 = round(256 mean)): with at most 512 bins either side the
-    // window lies strictly inside the coder's 2048-bin support, so it needs no edge cases
-    d.w0 = d.m.lower + 1024 - 16 * n + 1;
+    // window lies inside the coder's 2048-bin support, so it needs no edge cases.
+    //   n == 1: entry e of the head slot stands for bin w0 - 1 + e (e = 1 .. 31: mode - 15 .. mode + 15)
+    //   n > 1:  value r of the rows stands for bin w0 + r (r = 0 .. 32 n - 1)
+    d.w0 = d.m.lower + 1024 - (n > 1 ? 16 * n : 15);
     CoopGroup grp;
     grp.ones = __ballot_sync(kFull, n == 1);
     grp.multis = __ballot_sync(kFull, n > 1);
@@ -187,11 +217,9 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     constexpr int kSlots = Cfg::kSlots;
     extern __shared__ __align__(256) unsigned char s_raw[];
     uint64_t* const s_tab = reinterpret_cast<uint64_t*>(s_raw);                              // 256 B
-    int* const s_code = reinterpret_cast<int*>(s_raw + 512);                                 // 32 x 4 B (consumer only)
-    unsigned* const s_who = reinterpret_cast<unsigned*>(s_raw + 640);                        // 32 x 4 B (consumer only)
-    int* const s_toff = reinterpret_cast<int*>(s_raw + 768);                                 // 32 x 4 B (consumer only)
-    int4* const s_par = reinterpret_cast<int4*>(s_raw + 1024);                               // 32 x 48 B (consumer only)
-    // slots: [2][kSlots][32] CoopEntry from s_raw + kCoopSlotBase, in the HOME CTA (cluster rank 0)
+    // s_raw + 512: 32 x 4 B code (chunk offset, or the symbol itself for a scalar step); + 640: 32 x 4 B
+    // lane index of the matching entry (both: consumer only, addressed in the shared space)
+    // slots: [kBuffers][kSlots][32] CoopEntry from s_raw + kCoopSlotBase, in the HOME CTA (cluster rank 0)
     const ExpTab tab = stage_exp_table(s_tab);
 
     const int lane = threadIdx.x & 31;
@@ -209,7 +237,7 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     const float* const mean_s = mean + beg;
     const float* const scale_s = scale + beg;
     // every CTA of the cluster is running before anybody writes into the home CTA's shared memory
-    if constexpr (C > 1) cluster_sync_all();
+    if constexpr (C > 1) { cluster_arrive(); cluster_wait(); }
 
     // group g holds the symbols [len - 32 (g + 1), len - 32 g) that exist; lane j <-> the j-th of them
     auto load_group = [&](int g, float& mu, float& sc) -> bool {
@@ -231,6 +259,14 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         else if (Cfg::kHomeProducers && (warp & 3) != 3) producer = (warp >> 2) * 3 + (warp & 3);
     }
 
+    // Hand-over protocol.
+    //   C == 1: two buffers, one CTA barrier per group (producers: after tabulating g; consumer:
+    //       before decoding g), one more at the end.
+    //   C > 1: three buffers, cluster barrier phase g = "group g is tabulated and the consumer has
+    //       begun group g - 1" (i.e. finished g - 2, whose buffer group g + 1 reuses).  Producers
+    //       and idle warps arrive and wait once per group; the consumer arrives for phase g + 1
+    //       before decoding group g and waits for it afterwards.  Every thread of the cluster goes
+    //       through n_groups phases.
     if (producer >= 0) {
         // ------------------------------------------------------------------ producers
         uint32_t slot_base = (uint32_t)__cvta_generic_to_shared(s_raw) + (uint32_t)kCoopSlotBase;
@@ -239,9 +275,9 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         bool valid = load_group(0, mu, sc);
         for (int g = 0; g < n_groups; ++g) {
             CoopSymbol d;
-            const CoopGroup grp = coop_describe<C>(mu, sc, valid, lane, d);
+            const CoopGroup grp = coop_describe<C, true>(mu, sc, valid, lane, d);
             valid = load_group(g + 1, mu, sc);          // in flight during the evaluations
-            const uint32_t buf = slot_base + (uint32_t)(g & 1) * (uint32_t)(kSlots * 256);
+            const uint32_t buf = slot_base + (uint32_t)(g % Cfg::kBuffers) * (uint32_t)(kSlots * 256);
             // U tasks per pass: their evaluations are independent and interleave (a lone warp is
             // latency-bound on the ~35-deep dependency chain of one evaluation); a warp whose share
             // of the group is a single task evaluates just that one
@@ -258,8 +294,8 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                         j = (int)__fns(grp.ones, 0, t + 1);
                         c = 0;
                         sl = j;
-                    } else {                            // a chunk of a multi-chunk symbol
-                        sl = 32 + (t - grp.n_ones);
+                    } else {                            // a row of a wide window
+                        sl = t - grp.n_ones;
                         const unsigned owners = __ballot_sync(kFull, d.n > 1 && d.t_off <= sl);
                         j = owners ? 31 - __clz(owners) : 0;
                         c = sl - __shfl_sync(kFull, d.t_off, j);
@@ -271,35 +307,23 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                     mj[u].scale_d = shfl_f64(d.m.scale_d, j);
                     mj[u].rscale = shfl_f64(d.m.rscale, j);
                     mj[u].lower = __shfl_sync(kFull, d.m.lower, j);
-                    bins[u] = __shfl_sync(kFull, d.w0, j) - 1 + 32 * c + lane;
+                    const int w0 = __shfl_sync(kFull, d.w0, j);
+                    bins[u] = ns[u] > 1 ? w0 + 32 * c + lane : w0 - 1 + lane;
                 }
                 int v[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) v[u] = cdf_at(bins[u], mj[u], tab);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
+                    const int below = __shfl_up_sync(kFull, v[u], 1);
                     if (!on[u]) continue;
-                    const int c = cs[u], n = ns[u];
-                    // entry e of slot sl: byte address buf + 256 sl + 8 e; .p at +0, .v at +4
-                    const uint32_t row = buf + 256u * (uint32_t)slots[u] + 8u * (uint32_t)lane;
-                    // v is this entry's value and the next entry's p; the window's very first entry
-                    // has no left neighbour and can never be the symbol (empty interval p == v; the
-                    // chain tests (mod - p) < (v - p) in unsigned arithmetic)
-                    st_slot<C>(row + 4u, v[u]);
-                    if (lane < 31 || c + 1 < n) st_slot<C>(row + 8u, v[u]);   // lane 31: entry 0 of the next chunk
-                    if (lane == 0 && c == 0) st_slot<C>(row, v[u]);            // p == v: an empty interval
-                    if (n > 1) {
-                        // index (head slot): entry c = (last value of chunk c - 1, last value of chunk c), so that
-                        // p <= mod < v picks the chunk that holds the symbol; entries >= n never match
-                        const uint32_t index = buf + 256u * (uint32_t)js[u];
-                        if (lane == 31) {
-                            st_slot<C>(index + 8u * (uint32_t)c + 4u, v[u]);
-                            if (c + 1 < n) st_slot<C>(index + 8u * (uint32_t)(c + 1), v[u]);
-                        }
-                        if (c == 0) {
-                            if (lane == 0) st_slot<C>(index, -1);
-                            if (lane >= n) { st_slot<C>(index + 8u * (uint32_t)lane, kNever); st_slot<C>(index + 8u * (uint32_t)lane + 4u, kNever); }
-                        }
+                    if (ns[u] > 1) {
+                        // a row of a wide window: the values alone, 4 bytes per bin
+                        st_value<C>(buf + 8192u + 128u * (uint32_t)slots[u] + 4u * (uint32_t)lane, v[u]);
+                    } else {
+                        // head slot: entry e = (value of the lane below, own value); entry 0 has no left
+                        // neighbour and is the empty interval p == v
+                        st_entry<C>(buf + 256u * (uint32_t)slots[u] + 8u * (uint32_t)lane, lane ? below : v[u], v[u]);
                     }
                 }
             };
@@ -307,245 +331,268 @@ rans_decode_coop_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
                 if (t0 + Cfg::kProducers >= grp.total) run_tasks(std::integral_constant<int, 1>{}, t0);
                 else run_tasks(std::integral_constant<int, kCoopUnroll>{}, t0);
             }
-            group_sync<C>();   // group g tabulated; the consumer has finished group g - 1
+            if constexpr (C == 1) cta_sync();           // group g tabulated; the consumer has finished group g - 1
+            else { cluster_arrive(); cluster_wait(); }  // phase g
         }
-        group_sync<C>();       // pairs with the consumer's barrier after the last group
+        if constexpr (C == 1) cta_sync();               // pairs with the consumer's barrier after the last group
     } else if (!is_consumer) {
-        // ------------------------------------------------------------------ idle warps of the home CTA
-        for (int g = 0; g <= n_groups; ++g) group_sync<C>();
+        // ------------------------------------------------------------------ idle warps of the home CTA (C > 1)
+        for (int g = 0; g < n_groups; ++g) { cluster_arrive(); cluster_wait(); }
     } else {
         // ------------------------------------------------------------------ consumer
         const uint32_t* const wbase = packed + wbeg;
-        int wrem = too_long ? 0 : (int)wcount;          // unread words (w_next and w_after included); < 0: under-run
         const uint64_t st0 = states[stream];
         uint32_t hi = (uint32_t)(st0 >> 32), lo = (uint32_t)st0;
-        // the next two words of the stream wait in registers: a pull takes w_next, and the load that
-        // replaces w_after has a whole symbol or more to arrive before it can be wanted
-        uint32_t w_next = wrem > 0 ? __ldg(wbase + (wrem - 1)) : 0u;
-        uint32_t w_after = wrem > 1 ? __ldg(wbase + (wrem - 2)) : 0u;
+        // The stream's next 64 words wait in registers, one (wbuf) and one (wnxt) per lane: lane L of
+        // wbuf holds word wtop - 1 - L, of wnxt word wtop - 33 - L (words are consumed from the last
+        // emitted to the first; words before the stream's first read as 0).  k words of wbuf are
+        // consumed -- wtop - k are unread, negative once the stream has under-run --; the next one to
+        // pull is w_next = wbuf of lane k, fetched by shuffle right after each pull, so it is ready
+        // long before the following symbol can want it.  Before k can pass 31 the window slides (two
+        // shuffles and a select) and wnxt is reloaded -- a load with some 200 symbols to arrive.
+        int wtop = too_long ? 0 : (int)wcount, k = 0;
+        auto ldw = [&](int idx) -> uint32_t { return idx >= 0 ? __ldg(wbase + idx) : 0u; };
+        uint32_t wbuf = ldw(wtop - 1 - lane), wnxt = ldw(wtop - 33 - lane);
+        uint32_t w_next = __shfl_sync(kFull, wbuf, 0);
+        auto slide_words = [&]() {
+            const int s = lane + k;
+            const uint32_t a = __shfl_sync(kFull, wbuf, s), b = __shfl_sync(kFull, wnxt, s);   // source lane: s mod 32
+            wbuf = s < 32 ? a : b;
+            wtop -= k;
+            k = 0;
+            wnxt = ldw(wtop - 33 - lane);
+        };
         int32_t flags = too_long ? ST_TOO_LONG : 0;
         ParamGuard guard = guard_init();
         float* const x_s = x_out + beg;
-        // shared-space addresses (a generic pointer costs the shared-window base at every use)
+        // Shared memory is addressed in the shared space throughout: a generic pointer costs the
+        // shared-window base at every use, which in a cluster kernel is a special-register read.
         uint32_t sm = (uint32_t)__cvta_generic_to_shared(s_raw);
         asm volatile("" : "+r"(sm));
-        const uint32_t sm_who = sm + 640u;
-        auto sts_who = [&](int j, unsigned v) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sm_who + 4u * (uint32_t)j), "r"(v) : "memory");
+        const uint32_t sm_code = sm + 512u, sm_lane = sm + 640u;
+        auto sts32 = [&](uint32_t addr, int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); };
+        auto lds32 = [&](uint32_t addr) -> int {
+            int v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+            return v;
         };
         auto lds_entry = [&](uint32_t addr) -> CoopEntry {
             CoopEntry e;
             asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.p), "=r"(e.v) : "r"(addr) : "memory");
             return e;
         };
-
-        // rans.pyx:87-89, warp-uniform, in two halves: the selects sit on the chain, the count and
-        // the conditional load of the word after next do not
-        auto pull_state = [&]() -> uint32_t {
-            const uint32_t hi0 = hi;
-            hi = hi0 == 0u ? lo : hi0;
-            lo = hi0 == 0u ? w_next : lo;
-            return hi0;
+        // the lane whose entry is the symbol's notes its index (a speculative note that is taken back
+        // is simply overwritten)
+        auto note_lane = [&](int j, bool mine) {
+            if (mine) sts32(sm_lane + 4u * (uint32_t)j, lane);
         };
-        auto pull_refill = [&](uint32_t hi0) {
-            wrem -= hi0 == 0u ? 1 : 0;
-            w_next = hi0 == 0u ? w_after : w_next;
-            // if (hi0 == 0 && wrem >= 2) w_after = wbase[wrem - 2], as a predicated load
-            asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
-                         "setp.eq.u32 p, %1, 0;\n\t"
-                         "setp.gt.and.s32 p, %2, 1, p;\n\t"
-                         "mad.wide.s32 a, %2, 4, %3;\n\t"
-                         "@p ld.global.nc.u32 %0, [a+-8];\n\t}"
-                         : "+r"(w_after) : "r"(hi0), "r"(wrem), "l"(wbase));
+        // One tabulated entry against the state: this lane's candidate for the popped state and
+        // whether the entry is the symbol's.  rans.pyx:87-90,108 with the pull folded in:
+        // (h, l) is the state after the word pull, x = state >> 24, new = x freq + (mod - start).
+        struct Cand { uint32_t hi, lo; bool mine; };
+        auto candidate = [&](const CoopEntry e) -> Cand {
+            const bool pulled = hi == 0u;
+            const uint32_t h = pulled ? lo : hi, l = pulled ? w_next : lo;
+            const uint32_t dm = (l & kProbMask) - (uint32_t)e.p;                           // mod - start
+            const uint32_t fr = (uint32_t)(e.v - e.p);
+            const uint32_t xl = (h << 8) | (l >> 24), xh = h >> 24;
+            const uint64_t pr = (uint64_t)xl * fr + dm;
+            Cand c;
+            c.hi = (uint32_t)(pr >> 32) + xh * fr;
+            c.lo = (uint32_t)pr;
+            c.mine = dm < fr;                               // p <= mod < v, in unsigned arithmetic
+            return c;
         };
-        // The entry with p <= mod < v (and `live`), if this warp holds it, pops the state; everybody
-        // takes the result.  Returns the ballot of the entry's lane (0: nobody holds it, state
-        // unchanged).  A popped state is never 0 (state >> 24 >= 2^8), so the OR-reduction of the one
-        // lane's candidate is the broadcast.
-        auto take = [&](const CoopEntry e, int mod, bool live) -> unsigned {
-            const bool mine = live && e.p <= mod && mod < e.v;
-            const unsigned who = __ballot_sync(kFull, mine);
-            uint32_t chi = hi, clo = lo;
-            rans_pop32(chi, clo, (uint32_t)e.p, (uint32_t)(e.v - e.p));
-            const uint32_t rhi = __reduce_or_sync(kFull, mine ? chi : 0u);
-            const uint32_t rlo = __reduce_or_sync(kFull, mine ? clo : 0u);
-            if (who) { hi = rhi; lo = rlo; }
-            return who;
+        // After a symbol is decided: the word accounting of its pull (off the chain).
+        auto account_pull = [&](bool pulled) {
+            k += pulled ? 1 : 0;
+            w_next = __shfl_sync(kFull, wbuf, k);
         };
 
+        COOP_STAT(long long n_quad = 0, n_quad_fail = 0, n_one = 0, n_multi = 0, n_scalar = 0, n_slide = 0, t_wait = 0, t_setup = 0, t_quad = 0, t_one = 0, t_multi = 0, t_scalar = 0, t_store = 0;
+                  const long long t_begin = clock64();)
         float mu, sc;
         bool valid = load_group(0, mu, sc);
+        if constexpr (C > 1) {
+            if (n_groups > 0) { cluster_arrive(); cluster_wait(); }      // phase 0
+        }
         for (int g = 0; g < n_groups; ++g) {
+            COOP_STAT(const long long t_s0 = clock64();)
             CoopSymbol d;
-            const CoopGroup grp = coop_describe<C>(mu, sc, valid, lane, d);
+            const CoopGroup grp = coop_describe<C, false>(mu, sc, valid, lane, d);
             const int64_t base = len - 32 * (int64_t)(g + 1);
             const int j_lo = base < 0 ? (int)(-base) : 0;   // first group-slot that is a symbol
             valid = load_group(g + 1, mu, sc);
-            // for the symbols that leave the fast path: model, parameters, n, first chunk slot, window origin
-            s_par[3 * lane + 0] = make_int4(__double2loint(d.m.mean_d), __double2hiint(d.m.mean_d),
-                                            __double2loint(d.m.scale_d), __double2hiint(d.m.scale_d));
-            s_par[3 * lane + 1] = make_int4(__double2loint(d.m.rscale), __double2hiint(d.m.rscale), d.m.lower, d.w0);
-            s_par[3 * lane + 2] = make_int4(__float_as_int(d.mean), __float_as_int(d.scale), d.n, d.t_off);
-            s_code[lane] = 0;
-            s_toff[lane] = d.t_off;
+            sts32(sm_code + 4u * (uint32_t)lane, 0);
             __syncwarp();
-            group_sync<C>();   // group g tabulated
+            COOP_STAT(const long long t_s1 = clock64(); t_setup += t_s1 - t_s0;)
+            if constexpr (C == 1) cta_sync();                            // group g tabulated
+            else if (g + 1 < n_groups) cluster_arrive_relaxed();         // phase g + 1: group g - 1 is done
+            COOP_STAT(t_wait += clock64() - t_s1;)
             // A warp issues in order: whatever sits in front of an instruction in the stream delays
-            // it, needed or not.  So the common case -- a single-chunk symbol found in its window --
-            // gets a loop of its own with nothing else in it: the head entry is read one symbol ahead
-            // (fixed address: slot j), "single-chunk" is a bit of `ones`, the decoded value is worked
-            // out after the loop from the ballot each step leaves behind, and anything else LEAVES
-            // the loop, is decoded out of line, and the loop is entered again.
-            const uint32_t sm_slot = sm + (uint32_t)kCoopSlotBase + (uint32_t)(g & 1) * (uint32_t)(kSlots * 256) + 8u * (uint32_t)lane;
-            // One single-chunk symbol: this lane's candidate for the popped state and whether the
-            // lane's entry is the symbol's.  (h, l) is the state after the word pull.
-            struct Cand { uint32_t hi, lo; bool mine; };
-            auto candidate = [&](const CoopEntry e, uint32_t h, uint32_t l) -> Cand {
-                const uint32_t dm = (l & kProbMask) - (uint32_t)e.p;                           // mod - start
-                const uint32_t fr = (uint32_t)(e.v - e.p);
-                // pop as if this lane's entry were the one: x = state >> 24, new = x freq + (mod - start)
-                const uint32_t xl = (h << 8) | (l >> 24), xh = h >> 24;
-                const uint64_t pr = (uint64_t)xl * fr + dm;
-                Cand c;
-                c.hi = (uint32_t)(pr >> 32) + xh * fr;
-                c.lo = (uint32_t)pr;
-                c.mine = dm < fr;
-                return c;
+            // it, needed or not.  So the common case -- single-chunk symbols found in their windows
+            // -- runs up to four at a time in one straight line with nothing else in it:
+            // "single-chunk" is a bit of `ones`, the head entries sit at fixed addresses (slot j), the
+            // decoded value is worked out after the group from the lane index each step leaves
+            // behind, and anything else is decoded by a step of its own.
+            const uint32_t sm_slot = sm + (uint32_t)kCoopSlotBase + (uint32_t)(g % Cfg::kBuffers) * (uint32_t)(kSlots * 256) + 8u * (uint32_t)lane;
+            // R single-chunk symbols j, j - 1, ..: decoded optimistically (no branch, so nothing between
+            // one symbol's broadcast and the next one's search), and taken back as a whole if any of
+            // them fell outside its window.
+            auto run_singles = [&](auto rc, int j) -> bool {
+                constexpr int R = decltype(rc)::value;
+                const uint32_t a0 = sm_slot + 256u * (uint32_t)j;
+                CoopEntry es[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i) es[i] = lds_entry(a0 - 256u * (uint32_t)i);
+                const uint32_t s_hi = hi, s_lo = lo, s_next = w_next;
+                const int s_k = k;
+                uint32_t all_found = 1u;
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const bool pulled = hi == 0u;
+                    const Cand c = candidate(es[i]);
+                    const uint32_t rhi = __reduce_or_sync(kFull, c.mine ? c.hi : 0u);
+                    const uint32_t rlo = __reduce_or_sync(kFull, c.mine ? c.lo : 0u);
+                    hi = rhi;
+                    lo = rlo;
+                    // a popped state is never 0 (state >> 24 >= 2^8): both zero means nobody had the symbol
+                    all_found = (rhi | rlo) == 0u ? 0u : all_found;
+                    note_lane(j - i, c.mine);
+                    account_pull(pulled);
+                }
+                if (all_found) return true;
+                hi = s_hi; lo = s_lo; w_next = s_next; k = s_k;
+                return false;
             };
-            // A symbol without a window, or outside it: the lane kernel's step (guess, two exact
-            // evaluations, bracket search if the guess is off), by all lanes at once, with the model
-            // the group description already holds.
+            // The lane kernel's step by all lanes at once: a symbol without a window, or outside it.
+            // Mean, scale and window origin come from the owning lane; every lane builds the model.
             auto scalar_step = [&](int j) {
-                const int4 q0 = s_par[3 * j], q1 = s_par[3 * j + 1], q2 = s_par[3 * j + 2];
-                const uint32_t hi0 = pull_state();
-                pull_refill(hi0);
-                SymbolModel mj;
-                mj.mean_d = __hiloint2double(q0.y, q0.x);
-                mj.scale_d = __hiloint2double(q0.w, q0.z);
-                mj.rscale = __hiloint2double(q1.y, q1.x);
-                mj.lower = q1.z;
-                const int sym = decode_symbol_model(hi, lo, __int_as_float(q2.x), __int_as_float(q2.y), mj, tab, guard, flags);
-                s_code[j] = sym - (q1.w - 1);
-                sts_who(j, 1u);
+                const float mu_j = __shfl_sync(kFull, d.mean, j), sc_j = __shfl_sync(kFull, d.scale, j);
+                const int w0_j = __shfl_sync(kFull, d.w0, j);
+                const SymbolModel mj = make_model(mu_j, sc_j);
+                const bool pulled = hi == 0u;
+                const uint32_t h = pulled ? lo : hi, l = pulled ? w_next : lo;
+                hi = h;
+                lo = l;
+                account_pull(pulled);
+                const int sym = decode_symbol_model(hi, lo, mu_j, sc_j, mj, tab, guard, flags);
+                sts32(sm_code + 4u * (uint32_t)j, sym - (w0_j - 1));
+                sts32(sm_lane + 4u * (uint32_t)j, 0);
             };
-            // A multi-chunk symbol: its head slot indexes the chunks (entry c = last values of chunks
-            // c - 1 and c), so one ballot picks the chunk and a second one the entry.
-            auto multi_step = [&](int j) -> bool {
-                const CoopEntry index = lds_entry(sm_slot + 256u * (uint32_t)j);
-                const int t_off = s_toff[j];
-                const uint32_t hi0 = hi, h = hi0 == 0u ? lo : hi0, l = hi0 == 0u ? w_next : lo;   // pulled state
-                const int mod = (int)(l & kProbMask);
-                const unsigned which = __ballot_sync(kFull, index.p <= mod && mod < index.v);
-                const int c = __popc(which - 1u) & 31;       // one bit set: its index
-                const Cand cd = candidate(lds_entry(sm_slot + 256u * (uint32_t)(t_off + c)), h, l);
-                const unsigned who = __ballot_sync(kFull, cd.mine);
-                const uint32_t rhi = __reduce_or_sync(kFull, cd.mine ? cd.hi : 0u);
-                const uint32_t rlo = __reduce_or_sync(kFull, cd.mine ? cd.lo : 0u);
-                if (which == 0u || who == 0u) return false;
-                pull_refill(hi0);
-                sts_who(j, who);
-                s_code[j] = 32 * c;
-                hi = rhi;
-                lo = rlo;
+            // A symbol with a wide window: no search.  The continuous model is solved for the symbol
+            // (guess_symbol(), the lane kernel's first step: float arithmetic on mod), and the exact
+            // CDF values around the guess are READ from the rows instead of evaluated -- four of them,
+            // so a guess that is one bin off still decides.  Every lane does the same: nothing crosses
+            // lanes, and the chain is guess -> address -> load -> compare -> pop.
+            const uint32_t sm_rows = sm + (uint32_t)kCoopSlotBase + (uint32_t)(g % Cfg::kBuffers) * (uint32_t)(kSlots * 256) + 8192u;
+            // Its per-symbol constants sit in the owning lane's registers; they are fetched (six
+            // shuffles) at the end of the PREVIOUS wide step, or at the start of the group for the first
+            // one, so their latency is not in front of the chain.
+            struct WidePar { float m05, c2; int w0, bins; uint32_t row; int j; };
+            auto fetch_wide = [&](int jn) {
+                WidePar q;
+                const int src = jn < 0 ? 0 : jn;
+                q.m05 = __shfl_sync(kFull, d.mean * 256.0f - 0.5f, src);
+                q.c2 = __shfl_sync(kFull, d.scale * (256.0f * 0.693147181f), src);
+                q.w0 = __shfl_sync(kFull, d.w0, src);
+                q.bins = 32 * __shfl_sync(kFull, d.n, src);
+                q.row = sm_rows + 128u * (uint32_t)__shfl_sync(kFull, d.t_off, src);
+                q.j = jn;
+                return q;
+            };
+            auto next_wide = [&](int below) -> int {        // highest wide symbol under slot `below`; -1: none
+                const unsigned m = below > 0 ? grp.multis & ((1u << below) - 1u) : 0u;
+                return 31 - __clz((int)m);
+            };
+            WidePar wp = fetch_wide(31 - __clz((int)grp.multis));       // the group's first wide symbol (-1: none)
+            auto wide_step = [&](int j) -> bool {
+                const WidePar q = wp.j == j ? wp : fetch_wide(j);
+                const bool pulled = hi == 0u;
+                const uint32_t h = pulled ? lo : hi, l = pulled ? w_next : lo;
+                const uint32_t mod = l & kProbMask;
+                // The symbol from the sigmoid term alone: u0 = logit((mod - 1024) / A), s = ceil(m - 1/2 + c u0)
+                // (guess_symbol() without its Newton step: the linear term it corrects for moves the
+                // answer by less than a bin at these scales, and a guess one bin off still decides).
+                // Tails (mod - 1024 or A + 1024 - mod not positive) give a NaN or a wild index: not inside.
+                float lp, lq;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"((float)(mod - 1024u)));
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lq) : "f"((float)(16776192u - mod)));
+                const float sr = __fmaf_rn(q.c2, lp - lq, q.m05);
+                const int r = (int)(__float_as_uint(__fadd_ru(sr, 12582912.0f)) - 0x4b400000u) - q.w0;
+                const bool inside = (uint32_t)(r - 2) < (uint32_t)(q.bins - 3);       // r - 2 .. r + 1 are rows' values
+                const uint32_t a = q.row + 4u * (uint32_t)(inside ? r : 2);
+                const int v0 = lds32(a - 8u), v1 = lds32(a - 4u), v2 = lds32(a), v3 = lds32(a + 4u);
+                wp = fetch_wide(next_wide(j));              // for the next wide symbol of the group
+                // the symbol is the bin whose interval [CDF(b - 1), CDF(b)) holds mod: r, r - 1 or r + 1
+                const int mi = (int)mod;
+                const bool at = v1 <= mi && mi < v2, left = v0 <= mi && mi < v1, right = v2 <= mi && mi < v3;
+                if (!(inside && (at || left || right))) return false;
+                const int p = at ? v1 : (left ? v0 : v2), v = at ? v2 : (left ? v1 : v3);
+                hi = h;
+                lo = l;
+                rans_pop32(hi, lo, (uint32_t)p, (uint32_t)(v - p));
+                account_pull(pulled);
+                if (lane == 0) {
+                    sts32(sm_code + 4u * (uint32_t)j, r + (at ? 0 : (left ? -1 : 1)) + 1);   // x = w0 - 1 + code + lane note
+                    sts32(sm_lane + 4u * (uint32_t)j, 0);
+                }
                 return true;
             };
             int j = 31;
-            if (grp.total == 0) {
-                // nothing tabulated in this group (wide distributions): the lane kernel's step for every
-                // symbol, its model and parameters fetched from the owning lane one symbol ahead
-                struct Par { SymbolModel m; float mean, scale; };
-                auto par_of = [&](int k) {
-                    const int4 q0 = s_par[3 * k], q1 = s_par[3 * k + 1], q2 = s_par[3 * k + 2];
-                    Par q;
-                    q.m.mean_d = __hiloint2double(q0.y, q0.x);
-                    q.m.scale_d = __hiloint2double(q0.w, q0.z);
-                    q.m.rscale = __hiloint2double(q1.y, q1.x);
-                    q.m.lower = q1.z;
-                    q.mean = __int_as_float(q2.x);
-                    q.scale = __int_as_float(q2.y);
-                    return q;
-                };
-                Par pa = par_of(31), pb;
-#pragma unroll 1
-                for (; j >= j_lo; j -= 2) {
-                    pb = par_of(j > 0 ? j - 1 : 0);
-                    uint32_t hi0 = pull_state();
-                    pull_refill(hi0);
-                    const int sa = decode_symbol_model(hi, lo, pa.mean, pa.scale, pa.m, tab, guard, flags);
-                    if (lane == j) s_code[j] = sa - (d.w0 - 1);
-                    if (j - 1 < j_lo) { --j; break; }
-                    pa = par_of(j > 1 ? j - 2 : 0);
-                    hi0 = pull_state();
-                    pull_refill(hi0);
-                    const int sb = decode_symbol_model(hi, lo, pb.mean, pb.scale, pb.m, tab, guard, flags);
-                    if (lane == j - 1) s_code[j - 1] = sb - (d.w0 - 1);
-                }
-                // every symbol of such a group is "entry 0 of its code"
-                sts_who(lane, 1u);
-                j = j_lo - 1;
-            }
             while (j >= j_lo) {
-                const unsigned w = grp.ones << (31 - j);     // symbol j - k at bit 31 - k
-                if ((w >> 28) == 0xfu) {
-                    // Four single-chunk symbols in a row: decoded optimistically in one straight line
-                    // (no branch, so nothing between one symbol's broadcast and the next one's
-                    // search), and taken back if any of them fell outside its window.
-                    const uint32_t a0 = sm_slot + 256u * (uint32_t)j;
-                    const CoopEntry e0 = lds_entry(a0), e1 = lds_entry(a0 - 256u), e2 = lds_entry(a0 - 512u),
-                                    e3 = lds_entry(a0 - 768u);
-                    const uint32_t s_hi = hi, s_lo = lo, s_next = w_next, s_after = w_after;
-                    const int s_wrem = wrem;
-                    unsigned who[4];
-                    const CoopEntry es[4] = {e0, e1, e2, e3};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t hi0 = pull_state();
-                        const Cand c = candidate(es[k], hi, lo);
-                        who[k] = __ballot_sync(kFull, c.mine);
-                        const uint32_t rhi = __reduce_or_sync(kFull, c.mine ? c.hi : 0u);
-                        const uint32_t rlo = __reduce_or_sync(kFull, c.mine ? c.lo : 0u);
-                        pull_refill(hi0);
-                        hi = rhi;
-                        lo = rlo;
+                COOP_STAT(const long long t_i0 = clock64();)
+                if (k > 27) { slide_words(); COOP_STAT(++n_slide;) }
+                // single-chunk symbols in a row from j down, at most 4: a nibble table indexed by the top
+                // four bits of `ones` shifted to j (no find-leading-one, which is a slow-pipe operation).
+                // Plain compares and branches from here: an indirect branch (switch) costs the lone
+                // in-order warp 70 cycles more per step.
+                const unsigned top = (grp.ones << (31 - j)) >> 28;
+                const int run = (int)((0x4322111100000000ull >> (4u * top)) & 7ull);
+                if (run == 0) {
+                    if ((grp.multis >> j) & 1u) {
+                        if (wide_step(j)) { --j; COOP_STAT(++n_multi; t_multi += clock64() - t_i0;) continue; }
                     }
-                    if (who[0] != 0u && who[1] != 0u && who[2] != 0u && who[3] != 0u) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) sts_who(j - k, who[k]);
-                        j -= 4;
-                        continue;
-                    }
-                    hi = s_hi; lo = s_lo; w_next = s_next; w_after = s_after; wrem = s_wrem;
+                    scalar_step(j);
+                    COOP_STAT(++n_scalar; t_scalar += clock64() - t_i0;)
+                    --j;
+                    continue;
                 }
-                if (w & 0x80000000u) {
-                    // one single-chunk symbol
-                    const CoopEntry e = lds_entry(sm_slot + 256u * (uint32_t)j);
-                    const uint32_t hi0 = hi, h = hi0 == 0u ? lo : hi0, l = hi0 == 0u ? w_next : lo;
-                    const Cand c = candidate(e, h, l);
-                    const unsigned who = __ballot_sync(kFull, c.mine);
-                    const uint32_t rhi = __reduce_or_sync(kFull, c.mine ? c.hi : 0u);
-                    const uint32_t rlo = __reduce_or_sync(kFull, c.mine ? c.lo : 0u);
-                    if (who != 0u) {
-                        pull_refill(hi0);
-                        sts_who(j, who);
-                        hi = rhi;
-                        lo = rlo;
-                        --j;
-                        continue;
-                    }
-                } else if ((grp.multis >> j) & 1u) {
-                    if (multi_step(j)) { --j; continue; }
+                if (run >= 4) {
+                    if (run_singles(std::integral_constant<int, 4>{}, j)) { j -= 4; COOP_STAT(n_quad += 4; t_quad += clock64() - t_i0;) continue; }
+                    COOP_STAT(++n_quad_fail;)
+                } else if (run == 3) {
+                    if (run_singles(std::integral_constant<int, 3>{}, j)) { j -= 3; COOP_STAT(n_one += 3; t_one += clock64() - t_i0;) continue; }
+                } else if (run == 2) {
+                    if (run_singles(std::integral_constant<int, 2>{}, j)) { j -= 2; COOP_STAT(n_one += 2; t_one += clock64() - t_i0;) continue; }
                 }
+                // a run that failed as a whole is retried symbol by symbol; a symbol that is not in its
+                // window takes the lane kernel's step
+                if (run_singles(std::integral_constant<int, 1>{}, j)) { --j; COOP_STAT(++n_one; t_one += clock64() - t_i0;) continue; }
                 scalar_step(j);
+                COOP_STAT(++n_scalar; t_scalar += clock64() - t_i0;)
                 --j;
             }
+            COOP_STAT(const long long t_x0 = clock64();)
             __syncwarp();
             // s = (w0 - 1) + code + index of the matching lane
             if (lane >= j_lo)
-                x_s[base + lane] = (float)(d.w0 - 1 + s_code[lane] + __ffs((int)s_who[lane]) - 1) * 0.00390625f;   // s / 256., exact
+                x_s[base + lane] = (float)(d.w0 - 1 + lds32(sm_code + 4u * (uint32_t)lane) + lds32(sm_lane + 4u * (uint32_t)lane)) * 0.00390625f;   // s / 256., exact
             __syncwarp();
+            COOP_STAT(t_store += clock64() - t_x0;)
+            if constexpr (C > 1) {
+                COOP_STAT(const long long t_w0 = clock64();)
+                if (g + 1 < n_groups) cluster_wait();                    // group g + 1 tabulated
+                COOP_STAT(t_wait += clock64() - t_w0;)
+            }
         }
-        group_sync<C>();
+        if constexpr (C == 1) cta_sync();
+        COOP_STAT(if (lane == 0 && stream == 0) printf("coop stats C=%d: symbols %lld cycles %lld (%.1f/symbol) quad %lld (%.0f cyc) quad_fail %lld run<4 %lld (%.0f) multi %lld (%.0f) scalar %lld (%.0f) slides %lld; per group: wait %.0f setup %.0f store %.0f cycles\n",
+                         C, (long long)len, clock64() - t_begin, (double)(clock64() - t_begin) / (double)(len > 0 ? len : 1), n_quad, (double)t_quad / (double)(n_quad ? n_quad : 1), n_quad_fail,
+                         n_one, (double)t_one / (double)(n_one ? n_one : 1), n_multi, (double)t_multi / (double)(n_multi ? n_multi : 1), n_scalar, (double)t_scalar / (double)(n_scalar ? n_scalar : 1), n_slide,
+                         (double)t_wait / n_groups, (double)t_setup / n_groups, (double)t_store / n_groups);)
         if (lane == 0) {
+            const int wrem = wtop - k;                      // unread words; < 0: under-run
             flags |= guard_flags(guard);
             if (wrem < 0) flags |= ST_UNDERRUN;
             const uint64_t state = ((uint64_t)hi << 32) | lo;

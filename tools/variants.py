@@ -12,7 +12,7 @@ import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "finalproject-losslessimagecompression_b200")
 OUT = os.path.join(ROOT, "tools", "_build")
-VAR_SRC = ["rans_encode.cu", "rans_decode.cu", "cdf_tables.cu"]
+VAR_SRC = ["rans_encode.cu", "rans_decode.cu", "rans_decode_coop.cu", "cdf_tables.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-Xcompiler", "-fPIC"]
 
 
