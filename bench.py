@@ -932,15 +932,25 @@ def read_peaks():
         return {"hbm_gbs": 6650.0, "source": "fallback 6.65 TB/s (B200_PROFILING.md)"}
 
 
-def kernel_source_hash() -> str:
-    """SHA-256 over the CUDA sources the coder kernels are built from: profiles/traffic.json records it
-    when an ncu capture is summarised, and the bench quotes the capture only while it still matches."""
+KERNEL_SOURCES = {"rans_encode_lane_kernel": "rans_encode.cu", "rans_encode_kernel": "rans_encode.cu",
+                  "rans_decode_lane_kernel": "rans_decode.cu", "rans_decode_kernel": "rans_decode.cu",
+                  "rans_decode_coop_kernel": "rans_decode_coop.cu", "cdf_tables_kernel": "cdf_tables.cu"}
+
+
+def kernel_source_hash(kernel: str = "") -> str:
+    """SHA-256 over the CUDA sources `kernel` is built from (its .cu file, every shared header and the
+    build script with the nvcc flags; all sources when the kernel is not in KERNEL_SOURCES):
+    profiles/traffic.json records it when an ncu capture is summarised, and the bench quotes the
+    capture only while it still matches."""
     h = hashlib.sha256()
-    d = os.path.join(ROOT, "finalproject-losslessimagecompression_b200", "csrc")
+    pkg = os.path.join(ROOT, "finalproject-losslessimagecompression_b200")
+    d = os.path.join(pkg, "csrc")
+    own = KERNEL_SOURCES.get(kernel.split(" ")[0].split("<")[0])
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh")):
+        if name.endswith(".cuh") or (name.endswith(".cu") and (own is None or name == own)):
             h.update(name.encode())
             h.update(open(os.path.join(d, name), "rb").read())
+    h.update(open(os.path.join(pkg, "build.py"), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -950,7 +960,7 @@ def read_profile(kernel: str):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         rec = t[kernel.split(" ")[0]]
-        if rec.get("source_hash") != kernel_source_hash():
+        if rec.get("source_hash") != kernel_source_hash(kernel):
             return None
         return rec
     except Exception:

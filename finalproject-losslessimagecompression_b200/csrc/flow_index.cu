@@ -72,12 +72,52 @@ squeeze_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t b
     }
 }
 
+// s == 2, W a multiple of 8, 16-byte aligned tensors: one thread per 8 consecutive floats of a row of
+// the large tensor (two 16-byte accesses), which are 4 + 4 consecutive floats of the dx = 0 and
+// dx = 1 planes of the small one (one 16-byte access each).  Every access is a full-width vector
+// and every sector is touched once.
+__global__ void __launch_bounds__(256)
+squeeze2_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t batch, int64_t C,
+                    int64_t H, int64_t W, int direction) {
+    const int64_t w8 = W >> 3;                       // threads per row of the large tensor
+    const int64_t total = batch * C * H * w8;
+    const int64_t h2 = H >> 1, w2 = W >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t xq = i % w8;
+        const int64_t row = i / w8;                  // (b C + c) H + y
+        const int64_t y = row % H;
+        const int64_t bc = row / H;                  // b C + c
+        const int64_t big = row * W + xq * 8;
+        // plane (b, c 4 + dy 2 + dx) of the small tensor, row y / 2, columns 4 xq .. 4 xq + 3
+        const int64_t small0 = ((bc * 4 + (y & 1) * 2) * h2 + (y >> 1)) * w2 + xq * 4;
+        const int64_t small1 = small0 + h2 * w2;
+        if (direction > 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + big));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + big + 4));
+            *reinterpret_cast<float4*>(dst + small0) = make_float4(a.x, a.z, b.x, b.z);
+            *reinterpret_cast<float4*>(dst + small1) = make_float4(a.y, a.w, b.y, b.w);
+        } else {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(src + small0));
+            const float4 o = __ldg(reinterpret_cast<const float4*>(src + small1));
+            *reinterpret_cast<float4*>(dst + big) = make_float4(e.x, o.x, e.y, o.y);
+            *reinterpret_cast<float4*>(dst + big + 4) = make_float4(e.z, o.z, e.w, o.w);
+        }
+    }
+}
+
 cudaError_t launch_squeeze(const float* src, float* dst, int64_t batch, int64_t C, int64_t H,
                            int64_t W, int scale, int direction, cudaStream_t stream) {
     const int64_t n = batch * C * H * W;
     if (n <= 0) return cudaSuccess;
-    int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
+    if (scale == 2 && W % 8 == 0 && H % 2 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
+        int64_t blocks = (n / 8 + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        squeeze2_vec_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, batch, C, H, W, direction);
+        return cudaGetLastError();
+    }
+    int64_t blocks = (n + 255) / 256;
     if (blocks > cap) blocks = cap;
     squeeze_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, batch, C, H, W, scale, direction);
     return cudaGetLastError();

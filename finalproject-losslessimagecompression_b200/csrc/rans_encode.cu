@@ -126,24 +126,45 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
         const bool live = stream < n_streams;
         const int64_t beg = s_beg[lane], len = s_len[lane];
         uint64_t state = (live && init_states) ? init_states[stream] : kRansL;
-        int64_t wpos = beg;  // the stream's scratch region starts at its first symbol index
-        cta_sync();          // tile 0 complete
+        uint32_t* wp = scratch + beg;  // the stream's scratch region starts at its first symbol index
+        cta_sync();                    // tile 0 complete
         for (int64_t k = 0; k < n_tiles; ++k) {
             uint4(*tile)[kTile + 1] = s_tile[k & 1];
             const int64_t rem = len - k * kTile;
             const int cnt = rem >= kTile ? kTile : (rem > 0 ? (int)rem : 0);
-#pragma unroll 4
-            for (int j = 0; j < kTile; ++j) {
-                if (j < cnt) {
+            if (cnt == kTile) {
+                // whole row: no per-symbol test, and the entries are fetched four symbols ahead of
+                // their use, so the shared-memory latency is not on the state's dependency chain --
+                // what is left per symbol is renorm select -> convert -> multiply -> floor -> fix-up
+                uint4 e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = tile[lane][u];
+#pragma unroll
+                for (int j0 = 0; j0 < kTile; j0 += 4) {
+                    uint4 nx[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nx[u] = tile[lane][(j0 + 4 + u) & (kTile - 1)];   // last round: re-reads 0..3, unused
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t word;
+                        const bool emit = rans_push_rf(state, e[u].x, e[u].y, __hiloint2double((int)e[u].w, (int)e[u].z), word);
+                        if (emit) *wp = word;
+                        wp += emit ? 1 : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = nx[u];
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
                     const uint4 e = tile[lane][j];
                     uint32_t word;
-                    if (rans_push_rf(state, e.x, e.y, __hiloint2double((int)e.w, (int)e.z), word)) scratch[wpos++] = word;
+                    if (rans_push_rf(state, e.x, e.y, __hiloint2double((int)e.w, (int)e.z), word)) *wp++ = word;
                 }
             }
             cta_sync();  // tile k consumed; tile k+1 complete
         }
         if (live) {
-            counts[stream] = wpos - beg;
+            counts[stream] = (int64_t)(wp - (scratch + beg));
             states[stream] = state;
             status[stream] = s_flags[lane];
         }

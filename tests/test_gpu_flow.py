@@ -73,7 +73,8 @@ def test_permute_and_squeeze_match_reference_modules(golden):
     assert np.array_equal(extenddim.squeeze(x, 2, -1).cpu().numpy(), golden["n1.squeeze_bwd"])     # extenddim.py:31-37
 
 
-@pytest.mark.parametrize("shape,scale", [((3, 3, 64, 64), 2), ((2, 12, 32, 32), 2), ((2, 5, 9, 6), 3), ((4, 3, 27, 23), 1)])
+@pytest.mark.parametrize("shape,scale", [((3, 3, 64, 64), 2), ((2, 12, 32, 32), 2), ((2, 5, 9, 6), 3), ((4, 3, 27, 23), 1),
+                                         ((2, 4, 6, 12), 2), ((1, 2, 10, 8), 2), ((5, 3, 216, 184), 2)])
 def test_squeeze_against_torch_expression(shape, scale):
     from flic_b200 import extenddim
     x = torch.randn(shape, device="cuda")
@@ -94,6 +95,20 @@ def test_u8_grid_conversion(oracle):
     assert torch.equal(back, u8) and int(status.item()) == 0
     _, status = flows.grid_to_u8(torch.tensor([0.5, 0.3], device="cuda"))      # 128/256 and an off-grid value
     assert int(status.item()) != 0
+    # the 16-pixels-per-thread bodies: one bad value anywhere in a vector is reported; unaligned views
+    # take the scalar kernels and give the same answer
+    for bad in (0.5, 0.3, -1.0 / 256, 257.0 / 256):
+        g2 = grid[:1024].clone()
+        g2[517] = bad
+        assert int(flows.grid_to_u8(g2)[1].item()) != 0
+    big = torch.randint(0, 256, (4 * 3 * 64 * 64 + 3,), dtype=torch.uint8, device="cuda")
+    want = oracle.quantise_input_u8(big.cpu().numpy())
+    assert np.array_equal(flows.u8_to_grid(big).cpu().numpy(), want)
+    assert np.array_equal(flows.u8_to_grid(big[1:]).cpu().numpy(), want[1:])
+    gbig = torch.from_numpy(want).cuda()
+    for view in (gbig, gbig[1:], gbig[4:]):
+        back, status = flows.grid_to_u8(view)
+        assert torch.equal(back, big[big.numel() - view.numel():]) and int(status.item()) == 0
 
 
 # ---- the flow mirror against the reference's forward ----------------------------------------

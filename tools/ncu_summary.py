@@ -26,16 +26,11 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__pcsamp_warps_issue_stalled_mio_throttle", "smsp__pcsamp_warps_issue_stalled_branch_resolving"]
 
 
-def source_hash() -> str:
-    """Same digest as bench.py: kernel_source_hash (the CUDA sources the library is built from)."""
-    import hashlib
-    h = hashlib.sha256()
-    d = os.path.join(ROOT, "finalproject-losslessimagecompression_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh")):
-            h.update(name.encode())
-            h.update(open(os.path.join(d, name), "rb").read())
-    return h.hexdigest()[:16]
+def source_hash(kernel: str) -> str:
+    """bench.py's kernel_source_hash(kernel): the digest of the sources that kernel is built from."""
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.kernel_source_hash(kernel)
 
 
 def ncu(args):
@@ -79,7 +74,7 @@ def main():
                           "issue_slots_busy_pct": float(rec.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan").split()[0]),
                           "from": f"profiles/{tag}_ncu_full_summary.json",
                           # bench.py quotes these numbers only while the kernel sources still hash to this
-                          "source_hash": source_hash()}
+                          "source_hash": source_hash(short)}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     json.dump({"command": cmd, "symbols_per_launch": n_sym, "kernels": out},
               open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.json"), "w"), indent=1)
