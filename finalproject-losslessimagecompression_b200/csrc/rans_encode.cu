@@ -40,8 +40,11 @@ void note_coder_kernel(int which, const char* name) { g_last_kernel[which & 1].s
 constexpr int kRowBatch = 4;
 
 // Stream count (in warps of 32 streams per SM) from which the lane-per-stream kernel is used.
+// Measured with ImageNet64-shaped streams (tools/variants.py, -DFLIC_ENC_LANE_MIN_WARPS=...): the
+// tile kernel wins up to 5.2 warps per SM (94.8 against 77.6 G symbols/s), the two tie at 10.4, the
+// lane kernel wins from 15.6 (143 against 121) and by 36 % at 20.8 (159.5 against 117.7).
 #ifndef FLIC_ENC_LANE_MIN_WARPS
-#define FLIC_ENC_LANE_MIN_WARPS 24
+#define FLIC_ENC_LANE_MIN_WARPS 12
 #endif
 constexpr int kLaneKernelMinWarpsPerSm = FLIC_ENC_LANE_MIN_WARPS;
 
@@ -199,14 +202,17 @@ __device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_sr
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
-// 7 resident CTAs per SM (up to 73 registers): measured as fast as 9 (155 vs 156 G symbols/s) with
-// less DRAM over-fetch -- the more lanes stream concurrently, the more of the 64-byte DRAM bursts'
-// second halves are evicted from L2 before their lane asks for them (ncu: 23.5 / 22.0 / 20.4 GB
-// read at 9 / 7 / 6 CTAs for 19.3 GB of inputs).
+// 4 resident CTAs per SM (120 registers): the eight table evaluations of a block are independent, and
+// with the registers to keep all of them in flight the compiler hides the FP64 latencies inside one
+// warp, which pays more than the warps it costs -- 175.3 G symbols/s against 166.5 at 7 CTAs
+// (72 registers, an 8-byte spill), 170 at 6 (80), 167.6 at 5 (96), 166.8 at 8 (64); 3 and 2 compile
+// to the same 120-register code.  Fewer lanes streaming at once also means less DRAM over-fetch: the
+// more lanes, the more of the 64-byte DRAM bursts' second halves leave L2 before their lane asks for
+// them (ncu: 23.5 / 22.0 / 20.4 GB read at 9 / 7 / 6 CTAs for 19.3 GB of inputs).
 // Bookkeeping is 32-bit and per lane as in the decoder (rans_decode.cu): blocks q = 0 .. nb - 1,
 // only the first and the last can be partial, one running element index for the three arrays.
 #ifndef FLIC_ENC_MIN_BLOCKS
-#define FLIC_ENC_MIN_BLOCKS 7
+#define FLIC_ENC_MIN_BLOCKS 4
 #endif
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, FLIC_ENC_MIN_BLOCKS)
@@ -331,7 +337,7 @@ cudaError_t launch_rans_encode(const float* x, const float* mean, const float* s
     const int sh_x = (int)(((uintptr_t)x >> 2) & (kBlk - 1)), sh_m = (int)(((uintptr_t)mean >> 2) & (kBlk - 1));
     const int sh_s = (int)(((uintptr_t)scale >> 2) & (kBlk - 1));
     const bool same_phase = sh_x == sh_m && sh_x == sh_s && (((uintptr_t)x | (uintptr_t)mean | (uintptr_t)scale) & 3) == 0;
-    // a lane per stream fills the GPU from ~24 warps per SM upwards
+    // a lane per stream pays from ~12 warps of streams per SM upwards
     if (same_phase && blocks >= (int64_t)sm_count() * kLaneKernelMinWarpsPerSm) {
         const int64_t ctas = (blocks + kCoderWarps - 1) / kCoderWarps;
         rans_encode_lane_kernel<kCoderWarps><<<(unsigned)ctas, kCoderWarps * 32, 0, stream>>>(
