@@ -19,6 +19,7 @@ value   = inputs resident in HBM, CUDA-event timed.   e2e = same through the hos
 
 The same line carries, at N = 1, the other BASELINE.json configs and the reference-shaped calls:
   stream_count_sweep     device-timed encode / decode at 3 / 48 / 768 / 9936 / 98 304 / 393 216 streams
+  flow_kernels           achieved HBM GB/s of K1, K5, permute, squeeze, u8 <-> grid, log_prob sums
   list_api               the drop-in rans.encode / rans.decode (Python lists) on 1.5 M symbols
   configs                configs[0] (config1.yaml @32x32), configs[2] (resflows_smallpatch),
                          configs[3] (config_twolevel): whole model, compress + decompress
@@ -452,6 +453,7 @@ def run_flic(args) -> dict | None:
     full = None
     if world == 1 and not args.no_extras:
         for name, fn in (("stream_count_sweep", lambda: stream_count_sweep(dev)),
+                         ("flow_kernels", lambda: flow_kernels(dev)),
                          ("list_api", lambda: list_api(dev)),
                          ("configs", lambda: {leg: _leg_summary(run_model(args, leg, rank, world, dev, steps=2, warmup=3))
                                               for leg in ("config1", "patches", "twolevel")})):
@@ -605,6 +607,17 @@ def stream_count_sweep(dev):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.sweep(dev, reps=3)
+
+
+def flow_kernels(dev):
+    """Achieved HBM bandwidth of the kernels around the coder -- K1 (CDF tables), K5 (coupling add / round),
+    permute, squeeze, u8 <-> grid, fused log_prob sums -- on 32 768 ImageNet64-shaped images
+    (tools/prof_flowops.py: measure())."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_prof_flowops", os.path.join(ROOT, "tools", "prof_flowops.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.measure(32768, dev)
 
 
 def list_api(dev, n: int = 1_572_864):
