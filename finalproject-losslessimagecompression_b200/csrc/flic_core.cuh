@@ -540,6 +540,30 @@ FLIC_HD void cdf_pair(int s, const SymbolModel& m, ExpTab tab, int& c_lo, int& c
     c_lo = part1_at(a_lo, m, tab) + (s - m.lower);
 }
 
+// The same pair for the decoder's first try, without the limit on the argument: returns whether
+// both float arguments lie in [-128, 128], where the limited and the unlimited evaluation are the
+// same computation.  Outside (a guess more than 128 scale units from the mean, an overflowed
+// quotient) the values are meaningless but harmless -- nothing traps, the exp table index is
+// masked -- and the caller's bracket search, which evaluates with the limit, takes over.  Two
+// min/max per evaluation become one max and one compare per pair.
+#ifndef FLIC_TRY_UNLIMITED
+#define FLIC_TRY_UNLIMITED 1
+#endif
+FLIC_HD bool cdf_pair_try(int s, const SymbolModel& m, ExpTab tab, int& c_lo, int& c_hi) {
+#if FLIC_ARG_XU && FLIC_TRY_UNLIMITED
+    const double a_hi = half_bin_point(s);
+    const double a_lo = dsub(a_hi, 0.00390625);  // exact
+    const float f_hi = d2f(div_by_scale(dsub(a_hi, m.mean_d), m));
+    const float f_lo = d2f(div_by_scale(dsub(a_lo, m.mean_d), m));
+    c_hi = part1_from_arg((double)f_hi, tab) + (s - m.lower + 1);
+    c_lo = part1_from_arg((double)f_lo, tab) + (s - m.lower);
+    return fmaxf(fabsf(f_hi), fabsf(f_lo)) <= 128.0f;
+#else
+    cdf_pair(s, m, tab, c_lo, c_hi);
+    return true;
+#endif
+}
+
 struct SymbolTable {
     uint32_t start;  // CDF(x - 1/256)
     uint32_t freq;   // CDF(x) - start  (>= 1)
@@ -659,39 +683,37 @@ FLIC_HD void rans_pop32(uint32_t& hi, uint32_t& lo, uint32_t start, uint32_t fre
 // solved for g = mod + 0.5: start at u0 = logit(p0), p0 = (mod - 1024) / A (the sigmoid term alone,
 // window centre), then one Newton step on h(u) = A sig(u) + c u + (m - lower - mod),
 // u = (s + 0.5 - m) / c, m = 256 mean, c = 256 scale.  At u0 the sigmoid is p0 by construction, so
-// the step needs no exponential: A sig(u0) = P and A (1 - sig(u0)) = Q with the integers
-// P = mod - 1024 and Q = A - P, each kept >= 2 in the tails (h then uses the clamped value).
+// the step needs no exponential: A sig(u0) = P and A (1 - sig(u0)) = Q with P = mod - 1024,
+// Q = A - P, h(u0) = c u0 + (m - lower - 1024) and h'(u0) = P Q / A + c.  The step is taken in the
+// form  s + 0.5 = m + c u1 = m + c u0 (P Q) / (P Q + c A):  the offset m - lower - 1024 -- the
+// distance of the mean from the bin grid, at most half a count of the 2^24 -- is left out of h.
+// Half a count moves the answer by 0.5 / freq bins, so over a whole window this costs a wrong guess
+// (= a bracket search) with probability sum_bins (freq / 2^24) (0.5 / freq) = 6e-5 per symbol
+// whatever the distribution, and saves the conversion of `lower` and two additions on all others.
 // Three MUFU operations (two lg2, one rcp).  Only speed depends on the guess.
 FLIC_HD int guess_symbol(uint32_t mod, float mean, float scale, int lower) {
-    const float m = mean * 256.0f;
-    const float c = scale * 256.0f;
+    (void)lower;
     // P = mod - 1024, Q = A - P.  Neither is kept positive in the tails (mod < 1025 or
     // mod > A + 1023: 1.2e-4 of all slots) and the guess is not limited to the window: whatever comes
     // out there -- a wrapped integer, a NaN turned into an arbitrary index -- fails the caller's test
     // (in-window and CDF(g - 1) <= mod < CDF(g)) and the bracket search takes over.
-    const uint32_t P = mod - 1024u, Q = 16776192u - mod;
-    const float Pf = (float)P, Qf = (float)Q;
+    const float Pf = (float)(mod - 1024u);
+    const float Qf = 16775168.0f - Pf;                 // exact: integers below 2^24 (mod >= 1024)
+    const float cl = scale * 177.445678223f;           // 256 ln 2 scale: c u0 = cl (lg2 P - lg2 Q)
+    const float cA = scale * 4294443008.0f;            // 256 A scale (A 2^8 is a float)
+    const float mh = mean * 256.0f - 0.5f;             // the product is exact and shared with lower_of()
+    const float PQ = Pf * Qf;
 #if defined(__CUDA_ARCH__)
-    float lp, lq;   // flush-to-zero forms: no subnormal fix-ups (P, Q are integers)
+    float lp, lq, rd;   // flush-to-zero forms: no subnormal fix-ups (P, Q are integers)
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lp) : "f"(Pf));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lq) : "f"(Qf));
-    const float u0 = (lp - lq) * 0.693147181f;
-#else
-    const float u0 = (log2f(Pf) - log2f(Qf)) * 0.693147181f;
-#endif
-    const float h = ffma(c, u0, (m - (float)lower) - 1024.0f);
-    const float dh = ffma(Pf * (1.0f / 16775168.0f), Qf, c);
-#if defined(__CUDA_ARCH__)
-    float rdh;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdh) : "f"(dh));
-    const float u1 = ffma(-h, rdh, u0);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(PQ + cA));
+    const float sr = ffma((lp - lq) * cl, PQ * rd, mh);
     // ceil through a round-up add of 1.5 * 2^23 (exact integer in the low mantissa bits when
     // |sr| < 2^22; anything else lands outside the window)
-    const float sr = ffma(c, u1, m - 0.5f);
     return (int)(__float_as_uint(__fadd_ru(sr, 12582912.0f)) - 0x4b400000u);
 #else
-    const float u1 = ffma(-h, 1.0f / dh, u0);
-    const float sr = ceilf(ffma(c, u1, m - 0.5f));
+    const float sr = ceilf(ffma((log2f(Pf) - log2f(Qf)) * cl, PQ * (1.0f / (PQ + cA)), mh));
     return fabsf(sr) < 4.0e6f ? (int)sr : lower - 1;   // NaN too: outside the window
 #endif
 }
@@ -848,12 +870,12 @@ FLIC_HD int decode_symbol_model(uint32_t& hi, uint32_t& lo, float mean, float sc
     guard_note(guard, mean, scale);
     const int g = guess_symbol(mod, mean, scale, m.lower);
     int c_lo, c_hi;
-    cdf_pair(g, m, tab, c_lo, c_hi);
+    const bool args_ok = cdf_pair_try(g, m, tab, c_lo, c_hi);
     int s = g;
     // (a guess on the window's left edge whose CDF(g - 1) exceeds mod -- only a corrupt stream has
     // that -- is sorted out by the search function: the edge is virtual)
-    if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower))) {
-        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
+    if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower) && args_ok)) {
+        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, args_ok ? g : m.lower - 1, c_lo, c_hi);   // values without the argument limit are not evidence
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
     }
@@ -868,12 +890,12 @@ FLIC_HD int decode_symbol_lean(uint32_t& hi, uint32_t& lo, float mean, float sca
     guard_note(guard, mean, scale);
     const int g = guess_symbol(mod, mean, scale, m.lower);
     int c_lo, c_hi;
-    cdf_pair(g, m, tab, c_lo, c_hi);
+    const bool args_ok = cdf_pair_try(g, m, tab, c_lo, c_hi);
     int s = g;
     // (a guess on the window's left edge whose CDF(g - 1) exceeds mod -- only a corrupt stream has
     // that -- is sorted out by the search function: the edge is virtual)
-    if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower))) {
-        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi);
+    if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower) && args_ok)) {
+        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, args_ok ? g : m.lower - 1, c_lo, c_hi);   // values without the argument limit are not evidence
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
     }
