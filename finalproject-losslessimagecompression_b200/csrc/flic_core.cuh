@@ -540,12 +540,18 @@ FLIC_HD void cdf_pair(int s, const SymbolModel& m, ExpTab tab, int& c_lo, int& c
     c_lo = part1_at(a_lo, m, tab) + (s - m.lower);
 }
 
-// The same pair for the decoder's first try, without the limit on the argument: returns whether
-// both float arguments lie in [-128, 128], where the limited and the unlimited evaluation are the
-// same computation.  Outside (a guess more than 128 scale units from the mean, an overflowed
+// The same pair for the decoder's first try, without the limit of the argument to [-128, 128]:
+// returns whether both float arguments lie in [-680, 680].  Up to there the unlimited evaluation
+// gives what the limited one gives: inside [-128, 128] it is the same computation, and beyond it
+// both are saturated -- arg > 128: e <= e^-128, 1 + e == 1, part1 = A either way; arg < -128:
+// e >= e^128 (at most e^680 < 2^982: every double on the way is normal, neither the table's
+// exponent add nor round24()'s constant 2^(ex + 29) overflows), p A < 2^-160 rounds to the float
+// 0, part1 = 0 either way.  This keeps
+// distributions much narrower than a bin (|a - mean| / scale beyond 128 at the bin's own edges,
+// scale < 1.5e-5) on the fast path.  Outside [-680, 680] (scale below 5.7e-6, an overflowed
 // quotient) the values are meaningless but harmless -- nothing traps, the exp table index is
-// masked -- and the caller's bracket search, which evaluates with the limit, takes over.  Two
-// min/max per evaluation become one max and one compare per pair.
+// masked -- and the caller's search, which evaluates with the limit, starts from the guess without
+// them.  Two min/max per evaluation become one max and one compare per pair.
 #ifndef FLIC_TRY_UNLIMITED
 #define FLIC_TRY_UNLIMITED 1
 #endif
@@ -557,7 +563,7 @@ FLIC_HD bool cdf_pair_try(int s, const SymbolModel& m, ExpTab tab, int& c_lo, in
     const float f_lo = d2f(div_by_scale(dsub(a_lo, m.mean_d), m));
     c_hi = part1_from_arg((double)f_hi, tab) + (s - m.lower + 1);
     c_lo = part1_from_arg((double)f_lo, tab) + (s - m.lower);
-    return fmaxf(fabsf(f_hi), fabsf(f_lo)) <= 128.0f;
+    return fmaxf(fabsf(f_hi), fabsf(f_lo)) <= 680.0f;
 #else
     cdf_pair(s, m, tab, c_lo, c_hi);
     return true;
@@ -835,12 +841,12 @@ __device__ __forceinline__
 #else
 static inline
 #endif
-SymbolHit decode_symbol_search(uint32_t mod, float mean, float scale, ExpTab tab, int g, int c_lo, int c_hi) {
+SymbolHit decode_symbol_search(uint32_t mod, float mean, float scale, ExpTab tab, int g, int c_lo, int c_hi, bool evidence) {
     const SymbolModel m = make_model(mean, scale);
     SearchState st;
     st.lo = m.lower - 1; st.hi = m.lower + kWindow;
     st.c_lo = -1; st.c_hi = -1; st.step = 2; st.done = false;
-    if (!guess_in_window(g, m.lower)) {   // nothing is known yet: start from the nearest window end
+    if (!(guess_in_window(g, m.lower) && evidence)) {   // nothing is known yet: start at the guess / the nearest window end
         st.probe = clamp_to_window(g, m.lower);
     } else if (g == m.lower && c_hi > (int)mod) {   // the window's left edge is virtual: "not greater"
         SymbolHit h;
@@ -875,7 +881,7 @@ FLIC_HD int decode_symbol_model(uint32_t& hi, uint32_t& lo, float mean, float sc
     // (a guess on the window's left edge whose CDF(g - 1) exceeds mod -- only a corrupt stream has
     // that -- is sorted out by the search function: the edge is virtual)
     if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower) && args_ok)) {
-        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, args_ok ? g : m.lower - 1, c_lo, c_hi);   // values without the argument limit are not evidence
+        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi, args_ok);
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
     }
@@ -895,7 +901,7 @@ FLIC_HD int decode_symbol_lean(uint32_t& hi, uint32_t& lo, float mean, float sca
     // (a guess on the window's left edge whose CDF(g - 1) exceeds mod -- only a corrupt stream has
     // that -- is sorted out by the search function: the edge is virtual)
     if (!(c_lo <= (int)mod && c_hi > (int)mod && guess_in_window(g, m.lower) && args_ok)) {
-        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, args_ok ? g : m.lower - 1, c_lo, c_hi);   // values without the argument limit are not evidence
+        const SymbolHit h = decode_symbol_search(mod, mean, scale, tab, g, c_lo, c_hi, args_ok);
         s = h.s; c_lo = h.c_lo; c_hi = h.c_hi;
         if (s > m.lower + (kWindow - 1)) flags |= ST_NO_SYMBOL;
     }

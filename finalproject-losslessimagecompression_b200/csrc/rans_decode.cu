@@ -263,22 +263,24 @@ rans_decode_lane_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         cp_async_commit();
     };
     auto pull = [&]() {  // rans.pyx:87-89
-        const uint32_t hi0 = hi;                     // state < 2^32 iff the high word is zero
-        hi = hi0 == 0u ? lo : hi0;
-        lo = hi0 == 0u ? next_word : lo;
-        // if (hi0 == 0) { --wrem; if (wrem > 0) next_word = wbase[wrem - 1]; }, predicated: no
-        // divergent branch (with 32 lanes, some lane renormalises at nearly every symbol); the
-        // address is formed unconditionally (two shift-adds against selects under a predicate; zero
-        // extension is as good as sign extension for an address that is only used when wrem > 0)
+        // state < 2^32 iff the high word is zero: then (hi, lo) <- (lo, next_word), and
+        // { --wrem; if (wrem > 0) next_word = wbase[wrem - 1]; }, all predicated: no divergent
+        // branch (with 32 lanes, some lane renormalises at nearly every symbol), one comparison
+        // serving the selects and the decrement; the address is formed unconditionally (two
+        // shift-adds against selects under a predicate -- a wide multiply-add compiles to four
+        // instructions -- and zero extension is as good as sign extension for an address that is
+        // only used when wrem > 0)
         asm volatile("{\n\t.reg .pred p, q;\n\t.reg .u64 a;\n\t"
-                     "setp.eq.u32 p, %2, 0;\n\t"
-                     "@p add.s32 %1, %1, -1;\n\t"
-                     "setp.gt.and.s32 q, %1, 0, p;\n\t"
-                     "cvt.u64.u32 a, %1;\n\t"
+                     "setp.eq.u32 p, %0, 0;\n\t"
+                     "selp.b32 %0, %1, %0, p;\n\t"
+                     "selp.b32 %1, %2, %1, p;\n\t"
+                     "@p add.s32 %3, %3, -1;\n\t"
+                     "setp.gt.and.s32 q, %3, 0, p;\n\t"
+                     "cvt.u64.u32 a, %3;\n\t"
                      "shl.b64 a, a, 2;\n\t"
-                     "add.s64 a, a, %3;\n\t"
-                     "@q ld.global.nc.u32 %0, [a+-4];\n\t}"
-                     : "+r"(next_word), "+r"(wrem) : "r"(hi0), "l"(wbase));
+                     "add.s64 a, a, %4;\n\t"
+                     "@q ld.global.nc.u32 %2, [a+-4];\n\t}"
+                     : "+r"(hi), "+r"(lo), "+r"(next_word), "+r"(wrem) : "l"(wbase));
     };
 
     if (n_iter > 0) stage(0);

@@ -6,6 +6,9 @@
 `wide`  : logistic samples with scale from e^-12 to e^4 clipped to the window: exercises tiny
           frequencies (freq down to 1-3), saturated tails and window edges
 `edges` : symbols pinned to the first / last bins of the window
+`needle`: scales from e^-20 to e^-9 (2e-9 .. 1.2e-4, far below a bin): the CDF argument at the
+          symbol's own bin edges runs from ~30 to beyond 10^5, past the [-128, 128] limit of the
+          float argument and past what the decoder's unlimited first try accepts (680)
 """
 import numpy as np
 
@@ -39,6 +42,10 @@ def gen(kind: str, n: int, seed: int):
         lo = c_round(mean.astype(np.float64) * 256 - 1024)
         pick = rng.integers(0, 4, n)
         x = np.where(pick == 0, lo, np.where(pick == 1, lo + 2047, np.where(pick == 2, lo + 1, lo + 2046))) / 256
+    elif kind == "needle":
+        mean = rng.normal(0, 1.5, n).astype(np.float32)
+        scale = np.exp(rng.uniform(-20, -9, n)).astype(np.float32)
+        x = (c_round(mean.astype(np.float64) * 256) + rng.integers(-1, 2, n) * (rng.random(n) < 0.1)) / 256
     else:
         raise ValueError(kind)
     return x.astype(np.float32), mean, scale

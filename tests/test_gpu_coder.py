@@ -12,7 +12,7 @@ from _data import gen, ragged_offsets
 
 pytestmark = pytest.mark.gpu
 
-KINDS = ["test", "coder", "wide", "edges"]
+KINDS = ["test", "coder", "wide", "edges", "needle"]
 
 
 def _cuda(*arrs):

@@ -64,7 +64,7 @@ def test_reference_goldens(oracle, key, n, seed, kind):
     assert np.array_equal(rec[::-1], np.asarray(msg, np.float32))
 
 
-@pytest.mark.parametrize("kind", ["test", "coder", "wide", "edges"])
+@pytest.mark.parametrize("kind", ["test", "coder", "wide", "edges", "needle"])
 def test_oracle_equals_reference_build(oracle, kind):
     ref = oracle.ref_rans()
     if ref is None:
@@ -132,7 +132,7 @@ def test_expf_restatement_vs_host_libm(oracle):
             assert n_bad == 0
 
 
-@pytest.mark.parametrize("kind", ["test", "coder", "wide", "edges"])
+@pytest.mark.parametrize("kind", ["test", "coder", "wide", "edges", "needle"])
 def test_device_header_on_host_matches_oracle(oracle, host_harness, kind):
     H = host_harness
     n = 150_000
@@ -159,7 +159,9 @@ def test_device_header_on_host_matches_oracle(oracle, host_harness, kind):
     # the model): their `mod` falls in the 2 x 1026 values where the guess deliberately skips the
     # tail correction of its Newton step (5 instructions per symbol saved on everything else), so
     # the bracket search does the work there -- still half the reference's 13-14 evaluations
-    assert evals.value / n < (7.0 if kind == "edges" else 2.01)
+    # (`needle`: the tenth of its symbols that sit one bin off a far-narrower-than-a-bin mode are
+    # coded in the uniform floor, the same 2 x 1026 values)
+    assert evals.value / n < (7.0 if kind == "edges" else 3.2 if kind == "needle" else 2.01)
     out2 = np.zeros(n, np.float32)
     assert H.hh_decode_fast(_p(words, C.c_uint32), nw.value, state.value, _p(mean, C.c_float), _p(scale, C.c_float),
                             n, _p(out2, C.c_float), C.byref(end)) == 0
