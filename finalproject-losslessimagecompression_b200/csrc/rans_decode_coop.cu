@@ -67,6 +67,12 @@ namespace flic {
 #ifndef FLIC_CLUSTER_HOME_PRODUCERS
 #define FLIC_CLUSTER_HOME_PRODUCERS 1
 #endif
+#ifndef FLIC_COOP1_WARPS
+#define FLIC_COOP1_WARPS 8      // CTA-per-stream kernel: warps per CTA (producers + the consumer)
+#endif
+#ifndef FLIC_COOP1_SLOTS
+#define FLIC_COOP1_SLOTS 160    // and 32-entry slots per group buffer
+#endif
 constexpr int kCoopUnroll = FLIC_COOP_UNROLL;   // evaluations a producer warp interleaves
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCoopSlotBase = 2560;     // bytes of shared memory in front of the slots
@@ -79,12 +85,12 @@ struct CoopCfg {
     // C == 1: warps 0..6 produce, warp 7 is the consumer (more producers take issue slots from the
     // chain: 15 cost it 17 %); two CTAs fit an SM.  C > 1: 16 warps per CTA, the last one of the home
     // CTA is the consumer, alone on its sub-partition.
-    static constexpr int kWarps = C == 1 ? 8 : 16;
+    static constexpr int kWarps = C == 1 ? FLIC_COOP1_WARPS : 16;
     static constexpr int kConsumerWarp = kWarps - 1;
-    static constexpr int kHomeProducers = C == 1 ? 7 : (FLIC_CLUSTER_HOME_PRODUCERS ? 12 : 0);
+    static constexpr int kHomeProducers = C == 1 ? FLIC_COOP1_WARPS - 1 : (FLIC_CLUSTER_HOME_PRODUCERS ? 12 : 0);
     static constexpr int kProducers = kHomeProducers + (C - 1) * kWarps;   // per stream
     static constexpr int kBuffers = C == 1 ? 2 : 3;       // group buffers in flight
-    static constexpr int kSlots = C == 1 ? 160 : 296;     // 32-entry slots per group buffer
+    static constexpr int kSlots = C == 1 ? FLIC_COOP1_SLOTS : 296;     // 32-entry slots per group buffer
     static constexpr int kMaxChunks = C == 1 ? 4 : 32;    // 32-bin chunks per wide window
     static constexpr int kRows = (kSlots - 32) * 2;       // 128-byte rows (one chunk of a wide window each) behind the 32 head slots
     static constexpr size_t kSmemBytes = kCoopSlotBase + 8u * kBuffers * kSlots * 32;
