@@ -245,7 +245,13 @@ rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ m
     const int j_ends = (int)((beg + shift) & (kBlk - 1)) | (((int)((end - 1 + shift) & (kBlk - 1)) + 1) << 4);
 
     uint64_t state = (live && init_states) ? init_states[stream] : kRansL;
-    uint32_t* wp = scratch + beg;  // the stream's scratch region starts at its first symbol index
+    // the stream's scratch region starts at its first symbol index; the words are counted in 32 bits
+    // (a stream has fewer than 2^31 symbols and emits at most one word per symbol), so an emit is an
+    // address, a predicated store and a predicated increment -- a running 64-bit pointer costs two
+    // carries per symbol and the compiler keeps a second copy of it for the final count
+    uint32_t* wbase = scratch + beg;
+    asm volatile("" : "+l"(wbase));     // one register pair, not re-derived from the parameters at every emit
+    uint32_t wn = 0;
     int32_t flags = too_long ? ST_TOO_LONG : 0;
     ParamGuard guard = guard_init();
     constexpr int kArr = kLanes * kBlkPitch, kBuf = 3 * kArr;
@@ -282,7 +288,10 @@ rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ m
     };
     auto push = [&](const SymbolTable& e) {
         uint32_t word;
-        if (rans_push(state, e.start, e.freq, word)) *wp++ = word;
+        if (rans_push(state, e.start, e.freq, word)) {   // (wbase is opaque: say that it is global memory)
+            asm volatile("st.global.u32 [%0], %1;" ::"l"(wbase + wn), "r"(word) : "memory");
+            ++wn;
+        }
     };
 
     if (n_iter > 0) stage(0);
@@ -322,7 +331,7 @@ rans_encode_lane_kernel(const float* __restrict__ x, const float* __restrict__ m
         }
     }
     if (live) {
-        counts[stream] = (int64_t)(wp - (scratch + beg));
+        counts[stream] = (int64_t)wn;
         states[stream] = state;
         status[stream] = flags | guard_flags(guard);
     }
