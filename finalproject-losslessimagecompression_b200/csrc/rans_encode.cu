@@ -135,6 +135,13 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
             uint4(*tile)[kTile + 1] = s_tile[k & 1];
             const int64_t rem = len - k * kTile;
             const int cnt = rem >= kTile ? kTile : (rem > 0 ? (int)rem : 0);
+            // the tile's words are counted in 32 bits against the (opaque) pointer the tile starts at:
+            // an emit is address + predicated store + predicated increment, where a running 64-bit
+            // pointer advanced by a 0 / 1 select costs the lone consumer warp eight to ten
+            // instructions per symbol
+            uint32_t* wt = wp;
+            asm volatile("" : "+l"(wt));
+            uint32_t wn = 0;
             if (cnt == kTile) {
                 // whole row: no per-symbol test, and the entries are fetched four symbols ahead of
                 // their use, so the shared-memory latency is not on the state's dependency chain --
@@ -151,8 +158,10 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                     for (int u = 0; u < 4; ++u) {
                         uint32_t word;
                         const bool emit = rans_push_rf(state, e[u].x, e[u].y, __hiloint2double((int)e[u].w, (int)e[u].z), word);
-                        if (emit) *wp = word;
-                        wp += emit ? 1 : 0;
+                        if (emit) {
+                            asm volatile("st.global.u32 [%0], %1;" ::"l"(wt + wn), "r"(word) : "memory");
+                            ++wn;
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) e[u] = nx[u];
@@ -161,9 +170,13 @@ rans_encode_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                 for (int j = 0; j < cnt; ++j) {
                     const uint4 e = tile[lane][j];
                     uint32_t word;
-                    if (rans_push_rf(state, e.x, e.y, __hiloint2double((int)e.w, (int)e.z), word)) *wp++ = word;
+                    if (rans_push_rf(state, e.x, e.y, __hiloint2double((int)e.w, (int)e.z), word)) {
+                        asm volatile("st.global.u32 [%0], %1;" ::"l"(wt + wn), "r"(word) : "memory");
+                        ++wn;
+                    }
                 }
             }
+            wp += wn;
             cta_sync();  // tile k consumed; tile k+1 complete
         }
         if (live) {

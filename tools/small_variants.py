@@ -8,7 +8,7 @@ def one():
     import torch
     from flic_b200 import rans, _lib
     _lib.lib().flic_set_decode_kernel(0)
-    for streams, per in ((32, 16384), (768, 4096), (4736, 4096), (9936, 192)):
+    for streams, per in ((1, 400000), (3, 400000), (48, 16384), (768, 4096), (4736, 4096), (9936, 192)):
         n = streams * per
         g = torch.Generator(device="cuda").manual_seed(3)
         mean = torch.randint(-256, 257, (n,), device="cuda", generator=g).float() / 256
